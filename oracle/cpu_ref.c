@@ -1,0 +1,368 @@
+/*
+ * oracle/cpu_ref.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, single-file restatement of the reference (yanx27/PointASNL) point-set ops on the hot
+ * path.  It exists only so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs can check / time the algorithm on host cores.  The product path
+ * (pointasnl_b200/) never imports, links or calls anything in this directory.
+ *
+ * Parity status: the reference ships NO golden vectors or tests for these ops,
+ * so the restatement is pinned against the reference itself, compiled unmodified into oracle/_ref/
+ * by oracle/build_ref.sh:
+ *   - knn / three_nn / three_interpolate(+grad): pinned HERE (CPU) against ref_knn.so / ref_interp.so,
+ *     fixtures in tests/golden/ (tests/test_oracle_golden.py).
+ *   - fps / gather / ball query / group(+grad): the reference has GPU kernels only; pinned on the GPU
+ *     box against ref_sampling.so / ref_grouping.so (tests/test_gpu_parity.py) and through the golden
+ *     fixtures those runs produced (tests/golden/gpu_ref_*.npz).
+ *
+ * Every function cites the reference file:line it follows (paths relative to /root/reference).
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared (oracle/Makefile).  -ffp-contract=off matters:
+ * FMA use is written out explicitly with fmaf() where the reference's GPU build contracts, and is
+ * forbidden where the reference runs on x86 (no FMA in the baseline x86-64 ISA).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* number of OpenMP threads used over the batch dimension (1 = the faithful single-thread baseline) */
+static int g_threads = 1;
+void oracle_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
+int oracle_get_threads(void) { return g_threads; }
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* squared distance exactly as nvcc contracts the reference expression
+ *   (x2-x1)*(x2-x1)+(y2-y1)*(y2-y1)+(z2-z1)*(z2-z1)
+ * on the GPU: FMUL(dy*dy); FFMA(dx,dx,.); FFMA(dz,dz,.)  (SASS probe). */
+static inline float d2_gpu(float x1, float y1, float z1, float x2, float y2, float z2) {
+    float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+/* squared distance as the x86 builds evaluate it: ((dx*dx + dy*dy) + dz*dz), no FMA
+ * (tf_interpolate.cpp:73; nanoflann.hpp L2_Adaptor::evalMetric tail loop :341-344). */
+static inline float d2_x86(float x1, float y1, float z1, float x2, float y2, float z2) {
+    float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+    return (dx * dx + dy * dy) + dz * dz;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Farthest point sampling.  Follows tf_ops/sampling/tf_sampling_g.cu:105-170
+ * (farthestpointsamplingKernel, launched <<<32,512>>> at :203-205).
+ *   idx[0] = 0 (:114-116); temp init 1e38 (:118); per round d2 = min(d, temp[k]) (:144),
+ *   thread t scans k = t, t+512, ... keeping the first strict maximum (:146-149), then a pairwise tree
+ *   that keeps the LEFT operand on ties (:153-163).  Net tie rule: largest d2, then lowest (k mod 512),
+ *   then lowest k.  This closed form is cross-checked against oracle_fps_sim512 (a literal simulation of
+ *   the 512 threads and the tree) in tests/test_oracle.py.
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_fps(int b, int n, int m, const float *xyz, int *idx) {
+    if (m <= 0) return; /* :106 */
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i) {
+        const float *p = xyz + (size_t)i * n * 3;
+        int *o = idx + (size_t)i * m;
+        float *temp = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+        for (int k = 0; k < n; ++k) temp[k] = 1e38f;
+        int old = 0;
+        o[0] = 0;
+        for (int j = 1; j < m; ++j) {
+            float x1 = p[old * 3 + 0], y1 = p[old * 3 + 1], z1 = p[old * 3 + 2];
+            float best = -1.0f;
+            int besti = 0, bestt = 0;
+            for (int k = 0; k < n; ++k) {
+                float d = d2_gpu(x1, y1, z1, p[k * 3 + 0], p[k * 3 + 1], p[k * 3 + 2]);
+                float d2 = fminf(d, temp[k]);
+                temp[k] = d2;
+                int t = k & 511;
+                if (d2 > best || (d2 == best && (t < bestt || (t == bestt && k < besti)))) {
+                    best = d2;
+                    besti = k;
+                    bestt = t;
+                }
+            }
+            old = besti;
+            o[j] = old;
+        }
+        free(temp);
+    }
+}
+
+/* Literal simulation of the 512-thread block + tree reduce of tf_sampling_g.cu:123-168.
+ * Slow; used only to validate the closed-form tie rule of oracle_fps. */
+void oracle_fps_sim512(int b, int n, int m, const float *xyz, int *idx) {
+    if (m <= 0) return;
+    enum { BS = 512 };
+    for (int i = 0; i < b; ++i) {
+        const float *p = xyz + (size_t)i * n * 3;
+        int *o = idx + (size_t)i * m;
+        float *temp = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+        float dists[BS];
+        int dists_i[BS];
+        for (int k = 0; k < n; ++k) temp[k] = 1e38f;
+        int old = 0;
+        o[0] = 0;
+        for (int j = 1; j < m; ++j) {
+            float x1 = p[old * 3 + 0], y1 = p[old * 3 + 1], z1 = p[old * 3 + 2];
+            for (int t = 0; t < BS; ++t) {
+                int besti = 0;
+                float best = -1;
+                for (int k = t; k < n; k += BS) {
+                    float td = temp[k];
+                    float d = d2_gpu(x1, y1, z1, p[k * 3 + 0], p[k * 3 + 1], p[k * 3 + 2]);
+                    float d2 = fminf(d, td);
+                    if (d2 != td) temp[k] = d2;
+                    if (d2 > best) {
+                        best = d2;
+                        besti = k;
+                    }
+                }
+                dists[t] = best;
+                dists_i[t] = besti;
+            }
+            for (int u = 0; (1 << u) < BS; ++u) {
+                for (int t = 0; t < (BS >> (u + 1)); ++t) {
+                    int i1 = (t * 2) << u, i2 = (t * 2 + 1) << u;
+                    if (dists[i1] < dists[i2]) {
+                        dists[i1] = dists[i2];
+                        dists_i[i1] = dists_i[i2];
+                    }
+                }
+            }
+            old = dists_i[0];
+            o[j] = old;
+        }
+        free(temp);
+    }
+}
+
+/* gather_point: tf_sampling_g.cu:172-181.  out[b,j,:] = inp[b,idx[b,j],:]  (3 floats) */
+void oracle_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < m; ++j) {
+            int a = idx[(size_t)i * m + j];
+            for (int l = 0; l < 3; ++l) out[((size_t)i * m + j) * 3 + l] = inp[((size_t)i * n + a) * 3 + l];
+        }
+}
+/* gather_point_grad: tf_sampling_g.cu:183-192 (atomicAdd scatter; caller memset at tf_sampling.cpp:174).
+ * The oracle zero-fills and accumulates sequentially in index order (fp32). */
+void oracle_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g) {
+    memset(inp_g, 0, sizeof(float) * (size_t)b * n * 3);
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < m; ++j) {
+            int a = idx[(size_t)i * m + j];
+            for (int l = 0; l < 3; ++l) inp_g[((size_t)i * n + a) * 3 + l] += out_g[((size_t)i * m + j) * 3 + l];
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * query_ball_point: tf_ops/grouping/tf_grouping_g.cu:3-36.
+ *   scan support points in index order; stop once cnt == nsample (:16, tested BEFORE point k);
+ *   predicate max(sqrtf(d2),1e-20f) < radius (:24-25); on the first hit all nsample slots are filled
+ *   with k (:26-29); pts_cnt always written (:34).
+ *   Rows with no hit: the reference leaves idx untouched (uninitialised TF output); here and in the
+ *   product they are defined as 0 (documented deviation that no in-range query can observe).
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_ball_query(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
+                       int *idx, int *pts_cnt) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i) {
+        const float *s = xyz1 + (size_t)i * n * 3;
+        const float *q = xyz2 + (size_t)i * m * 3;
+        int *oi = idx + (size_t)i * m * nsample;
+        int *oc = pts_cnt + (size_t)i * m;
+        for (int j = 0; j < m; ++j) {
+            int cnt = 0;
+            for (int l = 0; l < nsample; ++l) oi[(size_t)j * nsample + l] = 0;
+            float x2 = q[j * 3 + 0], y2 = q[j * 3 + 1], z2 = q[j * 3 + 2];
+            for (int k = 0; k < n; ++k) {
+                if (cnt == nsample) break;
+                float x1 = s[k * 3 + 0], y1 = s[k * 3 + 1], z1 = s[k * 3 + 2];
+                /* reference writes (x2-x1): query minus support */
+                float d = fmaxf(sqrtf(d2_gpu(x1, y1, z1, x2, y2, z2)), 1e-20f);
+                if (d < radius) {
+                    if (cnt == 0)
+                        for (int l = 0; l < nsample; ++l) oi[(size_t)j * nsample + l] = k;
+                    oi[(size_t)j * nsample + cnt] = k;
+                    cnt += 1;
+                }
+            }
+            oc[j] = cnt;
+        }
+    }
+}
+
+/* group_point: tf_grouping_g.cu:40-57.  out[b,j,k,:] = points[b,idx[b,j,k],:] */
+void oracle_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < m; ++j)
+            for (int k = 0; k < nsample; ++k) {
+                int ii = idx[((size_t)i * m + j) * nsample + k];
+                memcpy(out + (((size_t)i * m + j) * nsample + k) * c, points + ((size_t)i * n + ii) * c,
+                       sizeof(float) * (size_t)c);
+            }
+}
+/* group_point_grad: tf_grouping_g.cu:61-78 (atomicAdd; caller memset tf_grouping.cpp:204). */
+void oracle_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                             float *grad_points) {
+    memset(grad_points, 0, sizeof(float) * (size_t)b * n * c);
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < m; ++j)
+            for (int k = 0; k < nsample; ++k) {
+                int ii = idx[((size_t)i * m + j) * nsample + k];
+                const float *g = grad_out + (((size_t)i * m + j) * nsample + k) * c;
+                float *d = grad_points + ((size_t)i * n + ii) * c;
+                for (int l = 0; l < c; ++l) d[l] += g[l];
+            }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * k nearest neighbours, the contract of knn_query (utils/pointasnl_util.py:22-30 ->
+ * utils/nearest_neighbors/knn_.cxx:104-135 -> nanoflann 1.2.3) and of knn_point / select_top_k
+ * (tf_ops/grouping/tf_grouping.py:48-73 -> selection_sort_gpu tf_grouping_g.cu:83-123).
+ *   distance = ((dx*dx + dy*dy) + dz*dz) in fp32 without FMA (nanoflann.hpp:341-344; exact search,
+ *   eps = 0, knn_.cxx:127); result ascending by distance (KNNResultSet::addPoint, nanoflann.hpp:115-139).
+ *   Ties: nanoflann keeps tree-visit order, selection_sort keeps the earliest position (strict '<',
+ *   tf_grouping_g.cu:110).  The oracle (and the product) define ties by ascending index, which equals
+ *   selection_sort exactly and equals nanoflann whenever no two candidates of a query are equidistant.
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_knn(int b, int n, int m, int k, const float *xyz1, const float *xyz2, int *idx, float *dist) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i) {
+        const float *s = xyz1 + (size_t)i * n * 3;
+        const float *q = xyz2 + (size_t)i * m * 3;
+        float *bd = (float *)malloc(sizeof(float) * (size_t)k);
+        int *bi = (int *)malloc(sizeof(int) * (size_t)k);
+        for (int j = 0; j < m; ++j) {
+            int cnt = 0;
+            float qx = q[j * 3 + 0], qy = q[j * 3 + 1], qz = q[j * 3 + 2];
+            for (int t = 0; t < n; ++t) {
+                float d = d2_x86(s[t * 3 + 0], s[t * 3 + 1], s[t * 3 + 2], qx, qy, qz);
+                if (cnt == k && !(d < bd[k - 1])) continue;
+                int pos = cnt < k ? cnt : k - 1;
+                while (pos > 0 && bd[pos - 1] > d) {
+                    bd[pos] = bd[pos - 1];
+                    bi[pos] = bi[pos - 1];
+                    --pos;
+                }
+                bd[pos] = d;
+                bi[pos] = t;
+                if (cnt < k) ++cnt;
+            }
+            for (int t = 0; t < k; ++t) {
+                idx[((size_t)i * m + j) * k + t] = t < cnt ? bi[t] : 0;
+                if (dist) dist[((size_t)i * m + j) * k + t] = t < cnt ? bd[t] : INFINITY;
+            }
+        }
+        free(bd);
+        free(bi);
+    }
+}
+
+/* selection_sort (select_top_k): tf_grouping_g.cu:83-123.  Full (b,m,n) outputs; the first k entries of
+ * each row are the k smallest in ascending order, the rest is the permuted remainder. */
+void oracle_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < m; ++j) {
+            const float *src = dist + ((size_t)i * m + j) * n;
+            float *pd = out + ((size_t)i * m + j) * n;
+            int *pi = outi + ((size_t)i * m + j) * n;
+            for (int s = 0; s < n; ++s) {
+                pd[s] = src[s];
+                pi[s] = s;
+            }
+            for (int s = 0; s < k; ++s) {
+                int mn = s;
+                for (int t = s + 1; t < n; ++t)
+                    if (pd[t] < pd[mn]) mn = t;
+                if (mn != s) {
+                    float tmp = pd[mn];
+                    pd[mn] = pd[s];
+                    pd[s] = tmp;
+                    int ti = pi[mn];
+                    pi[mn] = pi[s];
+                    pi[s] = ti;
+                }
+            }
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * three_nn: tf_ops/3d_interpolation/tf_interpolate.cpp:60-103.  Three smallest SQUARED distances
+ * (the sqrt at :72 is commented out), strict '<' cascade so the earliest index wins ties; d evaluated
+ * in float then widened to double for the compares (:73); best init 1e40 (-> +inf as float), idx init 0.
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i) {
+        const float *u = xyz1 + (size_t)i * n * 3;
+        const float *kn = xyz2 + (size_t)i * m * 3;
+        for (int j = 0; j < n; ++j) {
+            float x1 = u[j * 3 + 0], y1 = u[j * 3 + 1], z1 = u[j * 3 + 2];
+            double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+            int i1 = 0, i2 = 0, i3 = 0;
+            for (int k = 0; k < m; ++k) {
+                double d = d2_x86(x1, y1, z1, kn[k * 3 + 0], kn[k * 3 + 1], kn[k * 3 + 2]);
+                if (d < best1) {
+                    best3 = best2; i3 = i2;
+                    best2 = best1; i2 = i1;
+                    best1 = d; i1 = k;
+                } else if (d < best2) {
+                    best3 = best2; i3 = i2;
+                    best2 = d; i2 = k;
+                } else if (d < best3) {
+                    best3 = d; i3 = k;
+                }
+            }
+            size_t o = ((size_t)i * n + j) * 3;
+            dist[o] = (float)best1; idx[o] = i1;
+            dist[o + 1] = (float)best2; idx[o + 1] = i2;
+            dist[o + 2] = (float)best3; idx[o + 2] = i3;
+        }
+    }
+}
+
+/* three_interpolate: tf_interpolate.cpp:107-127.  out = p1*w1 + p2*w2 + p3*w3, x86 evaluation
+ * order ((p1*w1 + p2*w2) + p3*w3), no FMA. */
+void oracle_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                              float *out) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < n; ++j) {
+            size_t o = ((size_t)i * n + j) * 3;
+            float w1 = weight[o], w2 = weight[o + 1], w3 = weight[o + 2];
+            const float *p1 = points + ((size_t)i * m + idx[o]) * c;
+            const float *p2 = points + ((size_t)i * m + idx[o + 1]) * c;
+            const float *p3 = points + ((size_t)i * m + idx[o + 2]) * c;
+            float *d = out + ((size_t)i * n + j) * c;
+            for (int l = 0; l < c; ++l) d[l] = (p1[l] * w1 + p2[l] * w2) + p3[l] * w3;
+        }
+}
+/* three_interpolate_grad: tf_interpolate.cpp:131-153 (caller memset :258).  Sequential '+=' in j order. */
+void oracle_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                                   const float *weight, float *grad_points) {
+    memset(grad_points, 0, sizeof(float) * (size_t)b * m * c);
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < n; ++j) {
+            size_t o = ((size_t)i * n + j) * 3;
+            const float *g = grad_out + ((size_t)i * n + j) * c;
+            for (int t = 0; t < 3; ++t) {
+                float w = weight[o + t];
+                float *d = grad_points + ((size_t)i * m + idx[o + t]) * c;
+                for (int l = 0; l < c; ++l) d[l] += g[l] * w;
+            }
+        }
+}
