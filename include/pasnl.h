@@ -1,0 +1,154 @@
+/*
+ * pasnl.h -- C ABI of libpasnl_b200.so: the PointASNL point-set hot path as hand-written sm_100a CUDA.
+ *
+ * This is the drop-in boundary for the native launchers the reference's TF ops / Cython shim call
+ * (SURVEY.md section 8b).  Every entry point:
+ *   - is extern "C", takes plain pointers and sizes (DEVICE pointers unless stated), no torch types;
+ *   - keeps the argument order of the reference launcher it replaces, plus a trailing cudaStream_t (as void*);
+ *   - enqueues all work on that stream, never synchronises, never allocates, keeps no state between calls;
+ *   - writes every element of every output (grad entry points zero-fill their outputs themselves -- the
+ *     reference makes the caller cudaMemset: tf_sampling.cpp:174, tf_grouping.cpp:204, tf_interpolate.cpp:258);
+ *   - returns 0 on success, PASNL_EINVAL (-22) for bad arguments, or the positive cudaError_t of the launch.
+ * All tensors are dense row-major, last index fastest, float32 / int32, exactly as the reference ops take them.
+ * Paths cited below are relative to the reference repository (yanx27/PointASNL).
+ */
+#ifndef PASNL_H_
+#define PASNL_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PASNL_OK 0
+#define PASNL_EINVAL (-22)
+
+/* library identification: "pasnl-b200 <semver> sm_100a" */
+const char *pasnl_version(void);
+/* human-readable text for a return code of any entry point (static storage) */
+const char *pasnl_error_string(int code);
+
+/* ---------------------------------------------------------------- sampling (tf_ops/sampling) */
+
+/* Bytes of device scratch pasnl_fps needs for this shape (0 for every cloud that fits the register-resident
+ * kernels, n <= 65536).  Replaces the caller-allocated (32,n) `temp` of tf_sampling.cpp:115. */
+size_t pasnl_fps_workspace_bytes(int b, int n, int m);
+
+/* Farthest point sampling.  Replaces farthestpointsamplingLauncher(b,n,m,inp,temp,out)
+ * (tf_sampling_g.cu:203-205; kernel :105-170).  xyz (b,n,3) -> out_idx (b,m).  Bit-exact contract:
+ * out[.,0]=0; distance fmaf(dz,dz,fmaf(dx,dx,dy*dy)); running min; arg-max with ties broken by lowest
+ * (k mod 512), then lowest k.  workspace may be NULL when pasnl_fps_workspace_bytes()==0. */
+int pasnl_fps(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, void *stream);
+
+/* gather_point.  Replaces gatherpointLauncher(b,n,m,inp,idx,out) (tf_sampling_g.cu:206-208; kernel :172-181).
+ * inp (b,n,3), idx (b,m) -> out (b,m,3). */
+int pasnl_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream);
+/* gather_point_grad.  Replaces scatteraddpointLauncher(b,n,m,out_g,idx,inp_g) (tf_sampling_g.cu:209-211).
+ * out_g (b,m,3), idx (b,m) -> inp_g (b,n,3), zero-filled here. */
+int pasnl_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g, void *stream);
+
+/* Row gather with c channels: the tf.gather_nd of sampling() (utils/pointasnl_util.py:43-49) on features.
+ * src (b,n,c), idx (b,m) -> out (b,m,c); grad: out_g (b,m,c) -> src_g (b,n,c), zero-filled here. */
+int pasnl_gather_rows(int b, int n, int c, int m, const float *src, const int *idx, float *out, void *stream);
+int pasnl_gather_rows_grad(int b, int n, int c, int m, const float *out_g, const int *idx, float *src_g, void *stream);
+
+/* ---------------------------------------------------------------- grouping (tf_ops/grouping, nearest_neighbors) */
+
+/* query_ball_point.  Replaces queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)
+ * (tf_grouping_g.cu:125-128; kernel :3-36).  xyz1 (b,n,3) support, xyz2 (b,m,3) queries ->
+ * idx (b,m,nsample): first nsample support indices in ascending index order with
+ * max(sqrtf(d2),1e-20f) < radius, remaining slots padded with the first hit; pts_cnt (b,m) = hits (<= nsample).
+ * Rows without any hit are written as 0 (the reference leaves them uninitialised). */
+int pasnl_ball_query(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                     int *pts_cnt, void *stream);
+
+/* group_point / group_point_grad.  Replace groupPointLauncher(b,n,c,m,nsample,points,idx,out) and
+ * groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points) (tf_grouping_g.cu:133-141; kernels :40-78).
+ * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c); grad_points (b,n,c) zero-filled here. */
+int pasnl_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                      void *stream);
+int pasnl_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                           float *grad_points, void *stream);
+
+/* Exact k nearest neighbours.  Replaces cpp_knn_batch_omp(batch_data,batch_size,npts,dim,queries,nqueries,K,
+ * batch_indices) (utils/nearest_neighbors/knn_.h:17-19, knn_.cxx:104-135; dim fixed to 3, indices int32 as
+ * knn_query casts them, utils/pointasnl_util.py:30) and selectionSortLauncher's use by knn_point
+ * (tf_grouping.py:48-73).  xyz1 (b,n,3) support, xyz2 (b,m,3) queries -> idx (b,m,k) ascending by
+ * (squared distance ((dx*dx+dy*dy)+dz*dz) evaluated without FMA, index); dist (b,m,k) squared distances or NULL.
+ * Requires 1 <= k <= min(n, 128). */
+int pasnl_knn(int b, int n, int m, int k, const float *xyz1, const float *xyz2, int *idx, float *dist, void *stream);
+
+/* Fused neighbourhood gather of the SA-layer front end (utils/pointasnl_util.py:63-74 grouping() followed by
+ * :248-249): out[b,j,t,:] = [ xyz[b,i,:] - center[b,j,:] | xyz[b,i,:] | feat[b,i,:] ], i = idx[b,j,t].
+ * xyz (b,n,3); feat (b,n,c) or NULL with c=0; idx: m rows of nsample indices, consecutive rows idx_stride ints
+ * apart (>= nsample; lets a caller pass the first-k view of a wider index tensor); center (b,m,3) or NULL
+ * (then the leading 3 "relative" channels are omitted).  out (b,m,nsample,(center?3:0)+3+c). */
+int pasnl_group_concat(int b, int n, int c, int m, int nsample, const float *xyz, const float *feat, const int *idx,
+                       int idx_stride, const float *center, float *out, void *stream);
+/* Backward of pasnl_group_concat: grad_out (b,m,nsample,(has_center?3:0)+3+c) ->
+ * grad_xyz (b,n,3) (relative + absolute parts), grad_feat (b,n,c) (or NULL), grad_center (b,m,3) (or NULL,
+ * required iff has_center) = -sum_t grad_rel.  All outputs zero-filled here. */
+int pasnl_group_concat_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                            int idx_stride, int has_center, float *grad_xyz, float *grad_feat, float *grad_center,
+                            void *stream);
+
+/* ---------------------------------------------------------------- interpolation (tf_ops/3d_interpolation) */
+
+/* three_nn.  Replaces threenn_cpu(b,n,m,xyz1,xyz2,dist,idx) (tf_interpolate.cpp:60-103).
+ * xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) SQUARED distances ascending, idx (b,n,3);
+ * strict '<' cascade: the earliest index wins ties; missing neighbours (m<3): dist=+inf, idx=0. */
+int pasnl_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, void *stream);
+/* three_interpolate.  Replaces threeinterpolate_cpu(b,m,c,n,points,idx,weight,out) (tf_interpolate.cpp:107-127).
+ * points (b,m,c), idx (b,n,3), weight (b,n,3) -> out (b,n,c) = (p1*w1 + p2*w2) + p3*w3, no FMA (bit-exact). */
+int pasnl_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                            float *out, void *stream);
+/* three_interpolate_grad.  Replaces threeinterpolate_grad_cpu(b,n,c,m,grad_out,idx,weight,grad_points)
+ * (tf_interpolate.cpp:131-153).  grad_points (b,m,c) zero-filled here. */
+int pasnl_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                                 const float *weight, float *grad_points, void *stream);
+
+/* ---------------------------------------------------------------- Adaptive Sampling (utils/pointasnl_util.py:112-173) */
+
+/* SampleWeights attention core (pointasnl_util.py:137-146).  For each of `groups` (= B*S) neighbourhoods with k
+ * members and bottleneck width d:  W = softmax_rows(Q Kf^T * scale)  (k x k),  out = W V.
+ * q (groups,k,d); kv (groups,k,2d) -- the conv_kv_ds output unsliced, Kf = kv[...,:d], V = kv[...,d:];
+ * out (groups,k,d); attn (groups,k,k) = W, kept for the backward.  1 <= k <= 32, 1 <= d <= 256. */
+int pasnl_as_core_fwd(int groups, int k, int d, const float *q, const float *kv, float scale, float *out, float *attn,
+                      void *stream);
+int pasnl_as_core_bwd(int groups, int k, int d, const float *q, const float *kv, const float *attn, float scale,
+                      const float *grad_out, float *grad_q, float *grad_kv, void *stream);
+
+/* AdaptiveSampling re-sampling (pointasnl_util.py:155, 168-171).  w = softmax over the k axis of
+ * logits (groups,k,1+cg);  new_xyz[g,:] = sum_t w[g,t,0] * xyz[g,t,:];  new_feat[g,ch] = sum_t w[g,t,1+ch] * feat[g,t,ch].
+ * xyz / feat address member t of group g at  base + g*group_stride + t*member_stride  (strides in floats), so the
+ * first-k view of a grouped tensor needs no copy.  Outputs new_xyz (groups,3), new_feat (groups,cg) and
+ * w (groups,k,1+cg) (kept for the backward). */
+int pasnl_as_resample_fwd(int groups, int k, int cg, const float *logits, const float *xyz, long xyz_group_stride,
+                          long xyz_member_stride, const float *feat, long feat_group_stride, long feat_member_stride,
+                          float *new_xyz, float *new_feat, float *w, void *stream);
+/* Backward: grad_new_xyz (groups,3), grad_new_feat (groups,cg) -> grad_logits (groups,k,1+cg),
+ * grad_xyz (groups,k,3), grad_feat (groups,k,cg) (dense). */
+int pasnl_as_resample_bwd(int groups, int k, int cg, const float *w, const float *xyz, long xyz_group_stride,
+                          long xyz_member_stride, const float *feat, long feat_group_stride, long feat_member_stride,
+                          const float *grad_new_xyz, const float *grad_new_feat, float *grad_logits, float *grad_xyz,
+                          float *grad_feat, void *stream);
+
+/* ---------------------------------------------------------------- Point Non-Local cell (utils/pointasnl_util.py:175-219) */
+
+/* Attention core of PointNonLocalCell, mode='dot' (pointasnl_util.py:195-212), flash-style: for every cloud
+ * A = softmax_rows(Q Kf^T * scale) over the n support points and out = A V, without materialising A.
+ * q (b,s,d); kv (b,n,2d) -- the conv_kv output unsliced (Kf | V); out (b,s,d); lse (b,s) = row log-sum-exp of the
+ * scaled logits, kept for the backward.  d must be a multiple of 4, 4 <= d <= 128. */
+int pasnl_nl_core_fwd(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
+                      float *lse, void *stream);
+/* Bytes of device scratch pasnl_nl_core_bwd needs. */
+size_t pasnl_nl_core_bwd_workspace_bytes(int b, int s, int n, int d);
+/* Backward: grad_out (b,s,d) -> grad_q (b,s,d), grad_kv (b,n,2d). */
+int pasnl_nl_core_bwd(int b, int s, int n, int d, const float *q, const float *kv, const float *out, const float *lse,
+                      float scale, const float *grad_out, float *grad_q, float *grad_kv, void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASNL_H_ */

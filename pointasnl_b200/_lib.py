@@ -1,0 +1,105 @@
+"""ctypes binding of libpasnl_b200.so (the C ABI declared in include/pasnl.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  If the shared object is missing or a symbol
+cannot be resolved, importing an op raises immediately (``PasnlLibraryError``) -- it never degrades silently.
+Build it in-tree with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C pointasnl_b200/csrc``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpasnl_b200.so")
+
+c_int, c_long, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+P = c_void_p  # every device pointer travels as void*
+
+# name -> (restype, argtypes); mirrors include/pasnl.h one to one (tests/test_abi.py checks the two against each other)
+SIGNATURES = {
+    "pasnl_version": (ctypes.c_char_p, []),
+    "pasnl_error_string": (ctypes.c_char_p, [c_int]),
+    "pasnl_fps_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pasnl_fps": (c_int, [c_int, c_int, c_int, P, P, P, P]),
+    "pasnl_gather_point": (c_int, [c_int, c_int, c_int, P, P, P, P]),
+    "pasnl_gather_point_grad": (c_int, [c_int, c_int, c_int, P, P, P, P]),
+    "pasnl_gather_rows": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
+    "pasnl_gather_rows_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
+    "pasnl_ball_query": (c_int, [c_int, c_int, c_int, c_float, c_int, P, P, P, P, P]),
+    "pasnl_group_point": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "pasnl_group_point_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "pasnl_knn": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "pasnl_group_concat": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
+    "pasnl_group_concat_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P]),
+    "pasnl_three_nn": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+    "pasnl_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "pasnl_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "pasnl_as_core_fwd": (c_int, [c_int, c_int, c_int, P, P, c_float, P, P, P]),
+    "pasnl_as_core_bwd": (c_int, [c_int, c_int, c_int, P, P, P, c_float, P, P, P, P]),
+    "pasnl_as_resample_fwd": (c_int, [c_int, c_int, c_int, P, P, c_long, c_long, P, c_long, c_long, P, P, P, P]),
+    "pasnl_as_resample_bwd": (c_int, [c_int, c_int, c_int, P, P, c_long, c_long, P, c_long, c_long, P, P, P, P, P, P]),
+    "pasnl_nl_core_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, c_float, P, P, P]),
+    "pasnl_nl_core_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pasnl_nl_core_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P]),
+}
+
+
+class PasnlLibraryError(RuntimeError):
+    pass
+
+
+class PasnlError(RuntimeError):
+    """A pasnl_* entry point returned non-zero."""
+
+
+_lib = None
+launch_count = 0  # number of pasnl_* compute entry points invoked (bench.py reports it as gpu_launches)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PasnlLibraryError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library is not built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no fallback path.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise PasnlLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise PasnlLibraryError(f"{LIB_PATH} does not export {name}; rebuild the library") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def version():
+    return load().pasnl_version().decode()
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().pasnl_error_string(int(code)).decode()
+        raise PasnlError(f"{what} failed with code {code}: {msg}")
+
+
+def call(name, *args):
+    """Invoke a compute entry point and raise on a non-zero return code."""
+    global launch_count
+    launch_count += 1
+    check(getattr(load(), name)(*args), name)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,361 @@
+"""torch-facing wrappers of the C ABI: argument validation, output allocation, autograd.
+
+PyTorch is used here for device memory, streams and autograd plumbing only; every computation below is one
+``pasnl_*`` call into libpasnl_b200.so (include/pasnl.h).  No op has a CPU or pure-PyTorch fallback: a non-CUDA
+tensor is an error.
+
+Gradient contract = the reference's registrations: gather_point -> inp (tf_sampling.py:43-47),
+group_point -> points (tf_grouping.py:42-46), three_interpolate -> points only (tf_interpolate.py:29-34); no
+gradient for FPS / ball query / kNN / three_nn (ops.NoGradient at tf_sampling.py:22,57; tf_grouping.py:21,32;
+tf_interpolate.py:18).
+"""
+import torch
+
+from . import _lib
+
+_call = _lib.call
+_ptr = _lib.ptr
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: pointasnl_b200 has no CPU path (got device {t.device})")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _i32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: pointasnl_b200 has no CPU path (got device {t.device})")
+    if t.dtype != torch.int32:
+        if t.dtype in (torch.int64, torch.int16, torch.uint8):
+            t = t.to(torch.int32)
+        else:
+            raise ValueError(f"{name} must be an integer tensor, got {t.dtype}")
+    return t.contiguous()
+
+
+def _require(cond, msg):
+    if not cond:
+        raise ValueError(msg)  # mirrors TF's errors::InvalidArgument at the op boundary
+
+
+# ------------------------------------------------------------------ sampling
+def fps(npoint, inp):
+    inp = _f32(inp, "inp")
+    _require(int(npoint) > 0, "FarthestPointSample expects positive npoint")
+    _require(inp.dim() == 3 and inp.shape[2] == 3, "FarthestPointSample expects (batch_size,num_points,3) inp shape")
+    b, n, _ = inp.shape
+    _require(n >= 1, "FarthestPointSample expects at least one point per cloud")
+    out = torch.empty((b, int(npoint)), device=inp.device, dtype=torch.int32)
+    ws_bytes = _lib.load().pasnl_fps_workspace_bytes(b, n, int(npoint))
+    ws = torch.empty((ws_bytes,), device=inp.device, dtype=torch.uint8) if ws_bytes else None
+    _call("pasnl_fps", b, n, int(npoint), _ptr(inp), _ptr(ws), _ptr(out), _stream())
+    return out
+
+
+class GatherPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, idx):
+        inp, idx = _f32(inp, "inp"), _i32(idx, "idx")
+        _require(inp.dim() == 3 and inp.shape[2] == 3, "GatherPoint expects (batch_size,num_points,3) inp shape")
+        _require(idx.dim() == 2 and idx.shape[0] == inp.shape[0], "GatherPoint expects (batch_size,num_result) idx shape")
+        b, n, _ = inp.shape
+        m = idx.shape[1]
+        out = torch.empty((b, m, 3), device=inp.device, dtype=torch.float32)
+        _call("pasnl_gather_point", b, n, m, _ptr(inp), _ptr(idx), _ptr(out), _stream())
+        ctx.save_for_backward(idx)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, out_g):
+        (idx,) = ctx.saved_tensors
+        out_g = _f32(out_g, "out_g")
+        b, m = idx.shape
+        inp_g = torch.empty((b, ctx.n, 3), device=out_g.device, dtype=torch.float32)
+        _call("pasnl_gather_point_grad", b, ctx.n, m, _ptr(out_g), _ptr(idx), _ptr(inp_g), _stream())
+        return inp_g, None
+
+
+class GatherRows(torch.autograd.Function):
+    """out[b,j,:] = src[b,idx[b,j],:] for any channel count (tf.gather_nd of sampling(), pointasnl_util.py:43-49)."""
+
+    @staticmethod
+    def forward(ctx, src, idx):
+        src, idx = _f32(src, "src"), _i32(idx, "idx")
+        _require(src.dim() == 3, "gather expects (batch_size,num_points,channel) src shape")
+        _require(idx.dim() == 2 and idx.shape[0] == src.shape[0], "gather expects (batch_size,num_result) idx shape")
+        b, n, c = src.shape
+        m = idx.shape[1]
+        out = torch.empty((b, m, c), device=src.device, dtype=torch.float32)
+        _call("pasnl_gather_rows", b, n, c, m, _ptr(src), _ptr(idx), _ptr(out), _stream())
+        ctx.save_for_backward(idx)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, out_g):
+        (idx,) = ctx.saved_tensors
+        out_g = _f32(out_g, "out_g")
+        b, m, c = out_g.shape
+        src_g = torch.empty((b, ctx.n, c), device=out_g.device, dtype=torch.float32)
+        _call("pasnl_gather_rows_grad", b, ctx.n, c, m, _ptr(out_g), _ptr(idx), _ptr(src_g), _stream())
+        return src_g, None
+
+
+# ------------------------------------------------------------------ grouping
+def ball_query(radius, nsample, xyz1, xyz2):
+    xyz1, xyz2 = _f32(xyz1, "xyz1"), _f32(xyz2, "xyz2")
+    _require(float(radius) > 0, "QueryBallPoint expects positive radius")
+    _require(int(nsample) > 0, "QueryBallPoint expects positive nsample")
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0],
+             "QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape.")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = torch.empty((b, m, int(nsample)), device=xyz1.device, dtype=torch.int32)
+    cnt = torch.empty((b, m), device=xyz1.device, dtype=torch.int32)
+    _call("pasnl_ball_query", b, n, m, float(radius), int(nsample), _ptr(xyz1), _ptr(xyz2), _ptr(idx), _ptr(cnt),
+          _stream())
+    return idx, cnt
+
+
+class GroupPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        points, idx = _f32(points, "points"), _i32(idx, "idx")
+        _require(points.dim() == 3, "GroupPoint expects (batch_size, num_points, channel) points shape")
+        _require(idx.dim() == 3 and idx.shape[0] == points.shape[0],
+                 "GroupPoint expects (batch_size, npoints, nsample) idx shape")
+        b, n, c = points.shape
+        _, m, ns = idx.shape
+        out = torch.empty((b, m, ns, c), device=points.device, dtype=torch.float32)
+        _call("pasnl_group_point", b, n, c, m, ns, _ptr(points), _ptr(idx), _ptr(out), _stream())
+        ctx.save_for_backward(idx)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grad_out = _f32(grad_out, "grad_out")
+        b, m, ns, c = grad_out.shape
+        g = torch.empty((b, ctx.n, c), device=grad_out.device, dtype=torch.float32)
+        _call("pasnl_group_point_grad", b, ctx.n, c, m, ns, _ptr(grad_out), _ptr(idx), _ptr(g), _stream())
+        return g, None
+
+
+def knn(k, xyz1, xyz2, return_dist=False):
+    """k nearest support points (xyz1) of every query (xyz2), ascending (squared distance, index)."""
+    xyz1, xyz2 = _f32(xyz1, "xyz1"), _f32(xyz2, "xyz2")
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "knn expects (batch_size, ndataset, 3) support shape")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0],
+             "knn expects (batch_size, npoint, 3) query shape")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    k = int(k)
+    _require(1 <= k <= n, f"knn expects 1 <= k <= ndataset (k={k}, ndataset={n})")
+    _require(k <= 128, "knn supports k <= 128")
+    idx = torch.empty((b, m, k), device=xyz1.device, dtype=torch.int32)
+    dist = torch.empty((b, m, k), device=xyz1.device, dtype=torch.float32) if return_dist else None
+    _call("pasnl_knn", b, n, m, k, _ptr(xyz1), _ptr(xyz2), _ptr(idx), _ptr(dist), _stream())
+    return (dist, idx) if return_dist else idx
+
+
+class GroupConcat(torch.autograd.Function):
+    """[xyz[idx]-center | xyz[idx] | feat[idx]] in one pass (grouping() + translation normalisation + concat,
+    pointasnl_util.py:63-74,248-249).  ``idx`` may be a last-dim slice ``full_idx[:, :, :k]`` (no copy is made)."""
+
+    @staticmethod
+    def forward(ctx, xyz, feat, idx, center):
+        xyz = _f32(xyz, "xyz")
+        feat = _f32(feat, "feat") if feat is not None else None
+        center = _f32(center, "center") if center is not None else None
+        _require(idx.is_cuda and idx.dtype == torch.int32 and idx.dim() == 3, "idx must be a CUDA int32 (b,m,nsample) tensor")
+        _require(idx.stride(2) == 1 and idx.stride(0) == idx.shape[1] * idx.stride(1),
+                 "idx must be contiguous or a last-dim prefix slice of a contiguous tensor")
+        b, n, _ = xyz.shape
+        _, m, ns = idx.shape
+        c = 0 if feat is None else feat.shape[2]
+        if feat is not None:
+            _require(feat.shape[0] == b and feat.shape[1] == n, "feat must be (batch_size, ndataset, channel)")
+        if center is not None:
+            _require(tuple(center.shape) == (b, m, 3), "center must be (batch_size, npoint, 3)")
+        w = (3 if center is not None else 0) + 3 + c
+        out = torch.empty((b, m, ns, w), device=xyz.device, dtype=torch.float32)
+        _call("pasnl_group_concat", b, n, c, m, ns, _ptr(xyz), _ptr(feat), idx.data_ptr(), int(idx.stride(1)),
+              _ptr(center), _ptr(out), _stream())
+        ctx.save_for_backward(idx)
+        ctx.dims = (b, n, c, m, ns, center is not None, feat is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        b, n, c, m, ns, has_center, has_feat = ctx.dims
+        grad_out = _f32(grad_out, "grad_out")
+        dev = grad_out.device
+        g_xyz = torch.empty((b, n, 3), device=dev, dtype=torch.float32)
+        g_feat = torch.empty((b, n, c), device=dev, dtype=torch.float32) if has_feat else None
+        g_center = torch.empty((b, m, 3), device=dev, dtype=torch.float32) if has_center else None
+        _call("pasnl_group_concat_grad", b, n, c, m, ns, _ptr(grad_out), idx.data_ptr(), int(idx.stride(1)),
+              1 if has_center else 0, _ptr(g_xyz), _ptr(g_feat), _ptr(g_center), _stream())
+        return g_xyz, g_feat, None, g_center
+
+
+# ------------------------------------------------------------------ interpolation
+def three_nn(xyz1, xyz2):
+    xyz1, xyz2 = _f32(xyz1, "xyz1"), _f32(xyz2, "xyz2")
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ThreeNN expects (b,n,3) xyz1 shape.")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "ThreeNN expects (b,m,3) xyz2 shape.")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist = torch.empty((b, n, 3), device=xyz1.device, dtype=torch.float32)
+    idx = torch.empty((b, n, 3), device=xyz1.device, dtype=torch.int32)
+    _call("pasnl_three_nn", b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(idx), _stream())
+    return dist, idx
+
+
+class ThreeInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx, weight):
+        points, idx, weight = _f32(points, "points"), _i32(idx, "idx"), _f32(weight, "weight")
+        _require(points.dim() == 3, "ThreeInterpolate expects (b,m,c) points shape")
+        b, m, c = points.shape
+        _require(idx.dim() == 3 and idx.shape[0] == b and idx.shape[2] == 3, "ThreeInterpolate expects (b,n,3) idx shape")
+        n = idx.shape[1]
+        _require(tuple(weight.shape) == (b, n, 3), "ThreeInterpolate expects (b,n,3) weight shape")
+        out = torch.empty((b, n, c), device=points.device, dtype=torch.float32)
+        _call("pasnl_three_interpolate", b, m, c, n, _ptr(points), _ptr(idx), _ptr(weight), _ptr(out), _stream())
+        ctx.save_for_backward(idx, weight)
+        ctx.m = m
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        grad_out = _f32(grad_out, "grad_out")
+        b, n, c = grad_out.shape
+        g = torch.empty((b, ctx.m, c), device=grad_out.device, dtype=torch.float32)
+        _call("pasnl_three_interpolate_grad", b, n, c, ctx.m, _ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(g), _stream())
+        return g, None, None  # the reference registers a gradient w.r.t. points only (tf_interpolate.py:29-34)
+
+
+# ------------------------------------------------------------------ Adaptive Sampling cores
+class ASCore(torch.autograd.Function):
+    """softmax(Q Kf^T * scale) V per neighbourhood (pointasnl_util.py:137-146).  q (..., k, d), kv (..., k, 2d)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, scale):
+        q, kv = _f32(q, "q"), _f32(kv, "kv")
+        k, d = q.shape[-2], q.shape[-1]
+        _require(kv.shape[-2] == k and kv.shape[-1] == 2 * d and kv.shape[:-2] == q.shape[:-2], "kv must be (..., k, 2d)")
+        groups = q.numel() // (k * d)
+        out = torch.empty_like(q)
+        attn = torch.empty(q.shape[:-1] + (k,), device=q.device, dtype=torch.float32)
+        _call("pasnl_as_core_fwd", groups, k, d, _ptr(q), _ptr(kv), float(scale), _ptr(out), _ptr(attn), _stream())
+        ctx.save_for_backward(q, kv, attn)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, kv, attn = ctx.saved_tensors
+        grad_out = _f32(grad_out, "grad_out")
+        k, d = q.shape[-2], q.shape[-1]
+        groups = q.numel() // (k * d)
+        gq, gkv = torch.empty_like(q), torch.empty_like(kv)
+        _call("pasnl_as_core_bwd", groups, k, d, _ptr(q), _ptr(kv), _ptr(attn), ctx.scale, _ptr(grad_out), _ptr(gq),
+              _ptr(gkv), _stream())
+        return gq, gkv, None
+
+
+def _member_strides(t):
+    """(group_stride, member_stride) in floats of a (b, s, k, c) view whose channel dim is unit-stride and whose
+    (b, s) dims collapse to one group index."""
+    _require(t.dim() == 4 and t.stride(3) == 1 and t.stride(0) == t.shape[1] * t.stride(1),
+             "grouped tensor must be (b, s, k, c) with unit channel stride and collapsible (b, s)")
+    return int(t.stride(1)), int(t.stride(2))
+
+
+class ASResample(torch.autograd.Function):
+    """softmax over the k members + weighted re-sampling (pointasnl_util.py:155,168-171).
+    logits (b,s,k,1+cg); xyz (b,s,k,3) and feat (b,s,k,cg) may be strided views of wider grouped tensors."""
+
+    @staticmethod
+    def forward(ctx, logits, xyz, feat):
+        logits = _f32(logits, "logits")
+        _require(xyz.is_cuda and feat.is_cuda and xyz.dtype == torch.float32 and feat.dtype == torch.float32,
+                 "xyz / feat must be CUDA float32")
+        b, s, k, cw = logits.shape
+        cg = cw - 1
+        _require(tuple(xyz.shape) == (b, s, k, 3) and tuple(feat.shape) == (b, s, k, cg), "xyz / feat shape mismatch")
+        xgs, xms = _member_strides(xyz)
+        fgs, fms = _member_strides(feat)
+        groups = b * s
+        new_xyz = torch.empty((b, s, 3), device=logits.device, dtype=torch.float32)
+        new_feat = torch.empty((b, s, cg), device=logits.device, dtype=torch.float32)
+        w = torch.empty_like(logits)
+        _call("pasnl_as_resample_fwd", groups, k, cg, _ptr(logits), xyz.data_ptr(), xgs, xms, feat.data_ptr(), fgs, fms,
+              _ptr(new_xyz), _ptr(new_feat), _ptr(w), _stream())
+        ctx.save_for_backward(w, xyz, feat)
+        return new_xyz, new_feat
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_feat):
+        w, xyz, feat = ctx.saved_tensors
+        b, s, k, cw = w.shape
+        cg = cw - 1
+        g_xyz, g_feat = _f32(g_xyz, "g_xyz"), _f32(g_feat, "g_feat")
+        xgs, xms = _member_strides(xyz)
+        fgs, fms = _member_strides(feat)
+        gl = torch.empty_like(w)
+        gx = torch.empty((b, s, k, 3), device=w.device, dtype=torch.float32)
+        gf = torch.empty((b, s, k, cg), device=w.device, dtype=torch.float32)
+        _call("pasnl_as_resample_bwd", b * s, k, cg, _ptr(w), xyz.data_ptr(), xgs, xms, feat.data_ptr(), fgs, fms,
+              _ptr(g_xyz), _ptr(g_feat), _ptr(gl), _ptr(gx), _ptr(gf), _stream())
+        return gl, gx, gf
+
+
+# ------------------------------------------------------------------ Non-Local core
+class NLCore(torch.autograd.Function):
+    """softmax(Q Kf^T * scale) V over all support points without materialising the attention map
+    (pointasnl_util.py:195-212).  q (b,s,d), kv (b,n,2d) -> (b,s,d)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, scale):
+        q, kv = _f32(q, "q"), _f32(kv, "kv")
+        _require(q.dim() == 3 and kv.dim() == 3 and kv.shape[0] == q.shape[0] and kv.shape[2] == 2 * q.shape[2],
+                 "NL core expects q (b,s,d) and kv (b,n,2d)")
+        b, s, d = q.shape
+        n = kv.shape[1]
+        _require(d % 4 == 0 and 4 <= d <= 128, "NL core supports bottleneck widths d % 4 == 0, 4 <= d <= 128")
+        out = torch.empty_like(q)
+        lse = torch.empty((b, s), device=q.device, dtype=torch.float32)
+        _call("pasnl_nl_core_fwd", b, s, n, d, _ptr(q), _ptr(kv), float(scale), _ptr(out), _ptr(lse), _stream())
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, kv, out, lse = ctx.saved_tensors
+        grad_out = _f32(grad_out, "grad_out")
+        b, s, d = q.shape
+        n = kv.shape[1]
+        gq, gkv = torch.empty_like(q), torch.empty_like(kv)
+        ws_bytes = _lib.load().pasnl_nl_core_bwd_workspace_bytes(b, s, n, d)
+        ws = torch.empty((max(ws_bytes, 4),), device=q.device, dtype=torch.uint8)
+        _call("pasnl_nl_core_bwd", b, s, n, d, _ptr(q), _ptr(kv), _ptr(out), _ptr(lse), ctx.scale, _ptr(grad_out),
+              _ptr(gq), _ptr(gkv), _ptr(ws), _stream())
+        return gq, gkv, None

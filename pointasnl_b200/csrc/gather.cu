@@ -1,0 +1,353 @@
+// gather.cu -- irregular row gathers and their scatter-add backwards (HBM-bound kernels).
+//
+// Replaces gatherpointKernel / scatteraddpointKernel (reference tf_ops/sampling/tf_sampling_g.cu:172-192),
+// group_point_gpu / group_point_grad_gpu (tf_ops/grouping/tf_grouping_g.cu:40-78: one THREAD copies a whole
+// c-float row scalar by scalar, <<<b,256>>>), the tf.gather_nd calls of sampling()/grouping()
+// (utils/pointasnl_util.py:43-49,63-74) and threeinterpolate_cpu / _grad_cpu (tf_interpolate.cpp:107-153, one CPU
+// thread).  Here: one thread per 16-byte (or 4-byte) piece of an OUTPUT row, so stores are fully coalesced and the
+// source rows are read with the widest aligned vector the row pitch allows; grids cover all b*m*nsample rows.
+// Algorithmic traffic per launch: 4*rows (idx) + 4*rows*c (out) + 4*b*n*c (source, read once; re-reads hit L2).
+#include "common.cuh"
+
+using namespace pasnl;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// ---------------------------------------------------------------- generic row gather
+// out[row, :] = src[(row / rows_per_batch) * n + idx[row], :],  row in [0, rows)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) gather_rows_kernel(long rows, int rows_per_batch, int n, int c,
+                                                               const float *__restrict__ src,
+                                                               const int *__restrict__ idx, float *__restrict__ out) {
+    const int cv = c / VEC;
+    const long total = rows * cv;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
+        const long row = g / cv;
+        const int col = (int)(g - row * cv) * VEC;
+        const long bi = row / rows_per_batch;
+        const long srow = bi * n + __ldg(idx + row);
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<float4 *>(out + row * c + col) = ldg4(src + srow * c + col);
+        } else {
+            out[row * c + col] = __ldg(src + srow * c + col);
+        }
+    }
+}
+
+// grad_src[(row / rows_per_batch) * n + idx[row], :] += grad_out[row, :]
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) scatter_rows_add_kernel(long rows, int rows_per_batch, int n, int c,
+                                                                    const float *__restrict__ grad_out,
+                                                                    const int *__restrict__ idx,
+                                                                    float *__restrict__ grad_src) {
+    const int cv = c / VEC;
+    const long total = rows * cv;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
+        const long row = g / cv;
+        const int col = (int)(g - row * cv) * VEC;
+        const long bi = row / rows_per_batch;
+        const long srow = bi * n + __ldg(idx + row);
+        if constexpr (VEC == 4) {
+            const float4 v = ldg4(grad_out + row * c + col);
+            atomicAdd(reinterpret_cast<float4 *>(grad_src + srow * c + col), v);  // red.global.add.v4.f32 (sm_90+)
+        } else {
+            atomicAdd(grad_src + srow * c + col, __ldg(grad_out + row * c + col));
+        }
+    }
+}
+
+int grid_for(long work_items) {
+    long blocks = (work_items + kThreads - 1) / kThreads;
+    const long cap = 148L * 32;  // grid-stride beyond ~32 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+int gather_rows(long rows, int rows_per_batch, int n, int c, const float *src, const int *idx, float *out,
+                cudaStream_t st) {
+    if (rows == 0 || c == 0) return PASNL_OK;
+    if (c % 4 == 0 && aligned16(src) && aligned16(out)) {
+        gather_rows_kernel<4><<<grid_for(rows * (c / 4)), kThreads, 0, st>>>(rows, rows_per_batch, n, c, src, idx, out);
+    } else {
+        gather_rows_kernel<1><<<grid_for(rows * c), kThreads, 0, st>>>(rows, rows_per_batch, n, c, src, idx, out);
+    }
+    return pasnl_launch_status();
+}
+
+int scatter_rows_add(long rows, int rows_per_batch, int n, int c, long src_rows, const float *grad_out, const int *idx,
+                     float *grad_src, cudaStream_t st) {
+    if (src_rows * c > 0) {
+        cudaError_t e = cudaMemsetAsync(grad_src, 0, sizeof(float) * (size_t)src_rows * c, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (rows == 0 || c == 0) return PASNL_OK;
+    if (c % 4 == 0 && aligned16(grad_out) && aligned16(grad_src)) {
+        scatter_rows_add_kernel<4>
+            <<<grid_for(rows * (c / 4)), kThreads, 0, st>>>(rows, rows_per_batch, n, c, grad_out, idx, grad_src);
+    } else {
+        scatter_rows_add_kernel<1>
+            <<<grid_for(rows * c), kThreads, 0, st>>>(rows, rows_per_batch, n, c, grad_out, idx, grad_src);
+    }
+    return pasnl_launch_status();
+}
+
+// ---------------------------------------------------------------- fused SA-layer neighbourhood gather
+// out[row, :] = [ xyz[i] - center[q] | xyz[i] | feat[i] ]   (leading part only if center != nullptr)
+// One thread per output float: consecutive threads write consecutive floats (coalesced stores); the feature
+// part of a row is a contiguous read of the source row.
+__global__ void __launch_bounds__(kThreads) group_concat_kernel(long rows, int m, int nsample, int n, int c,
+                                                                int idx_stride, const float *__restrict__ xyz,
+                                                                const float *__restrict__ feat,
+                                                                const int *__restrict__ idx,
+                                                                const float *__restrict__ center,
+                                                                float *__restrict__ out) {
+    const int lead = center ? 3 : 0;
+    const int w = lead + 3 + c;
+    const long total = rows * w;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
+        const long row = g / w;  // (b, j, t) flattened
+        const int col = (int)(g - row * w);
+        const long q = row / nsample;  // (b, j) flattened
+        const int t = (int)(row - q * nsample);
+        const long bi = q / m;
+        const long srow = bi * n + __ldg(idx + q * idx_stride + t);
+        float v;
+        if (col < lead) {
+            v = __fsub_rn(__ldg(xyz + srow * 3 + col), __ldg(center + q * 3 + col));
+        } else if (col < lead + 3) {
+            v = __ldg(xyz + srow * 3 + (col - lead));
+        } else {
+            v = __ldg(feat + srow * c + (col - lead - 3));
+        }
+        out[g] = v;
+    }
+}
+
+// Backward: one thread per grad_out float.  Relative and absolute xyz parts both land in grad_xyz[i];
+// grad_center[q] accumulates minus the relative part.
+__global__ void __launch_bounds__(kThreads) group_concat_grad_kernel(long rows, int m, int nsample, int n, int c,
+                                                                     int idx_stride, int has_center,
+                                                                     const float *__restrict__ grad_out,
+                                                                     const int *__restrict__ idx,
+                                                                     float *__restrict__ grad_xyz,
+                                                                     float *__restrict__ grad_feat,
+                                                                     float *__restrict__ grad_center) {
+    const int lead = has_center ? 3 : 0;
+    const int w = lead + 3 + c;
+    const long total = rows * w;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
+        const long row = g / w;
+        const int col = (int)(g - row * w);
+        const long q = row / nsample;
+        const int t = (int)(row - q * nsample);
+        const long bi = q / m;
+        const long srow = bi * n + __ldg(idx + q * idx_stride + t);
+        const float v = __ldg(grad_out + g);
+        if (col < lead) {
+            atomicAdd(grad_xyz + srow * 3 + col, v);
+            atomicAdd(grad_center + q * 3 + col, -v);
+        } else if (col < lead + 3) {
+            atomicAdd(grad_xyz + srow * 3 + (col - lead), v);
+        } else {
+            atomicAdd(grad_feat + srow * c + (col - lead - 3), v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- three_interpolate
+// out[row, :] = (p1*w1 + p2*w2) + p3*w3 with separate roundings (the x86 reference has no FMA): bit-exact.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) three_interp_kernel(long rows, int n, int m, int c,
+                                                                const float *__restrict__ points,
+                                                                const int *__restrict__ idx,
+                                                                const float *__restrict__ weight,
+                                                                float *__restrict__ out) {
+    const int cv = c / VEC;
+    const long total = rows * cv;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
+        const long row = g / cv;
+        const int col = (int)(g - row * cv) * VEC;
+        const long bi = row / n;
+        const float w1 = __ldg(weight + row * 3), w2 = __ldg(weight + row * 3 + 1), w3 = __ldg(weight + row * 3 + 2);
+        const float *p1 = points + (bi * m + __ldg(idx + row * 3)) * c + col;
+        const float *p2 = points + (bi * m + __ldg(idx + row * 3 + 1)) * c + col;
+        const float *p3 = points + (bi * m + __ldg(idx + row * 3 + 2)) * c + col;
+        if constexpr (VEC == 4) {
+            const float4 a = ldg4(p1), b4 = ldg4(p2), d = ldg4(p3);
+            float4 r;
+            r.x = __fadd_rn(__fadd_rn(__fmul_rn(a.x, w1), __fmul_rn(b4.x, w2)), __fmul_rn(d.x, w3));
+            r.y = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w1), __fmul_rn(b4.y, w2)), __fmul_rn(d.y, w3));
+            r.z = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w1), __fmul_rn(b4.z, w2)), __fmul_rn(d.z, w3));
+            r.w = __fadd_rn(__fadd_rn(__fmul_rn(a.w, w1), __fmul_rn(b4.w, w2)), __fmul_rn(d.w, w3));
+            *reinterpret_cast<float4 *>(out + row * c + col) = r;
+        } else {
+            out[row * c + col] =
+                __fadd_rn(__fadd_rn(__fmul_rn(__ldg(p1), w1), __fmul_rn(__ldg(p2), w2)), __fmul_rn(__ldg(p3), w3));
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) three_interp_grad_kernel(long rows, int n, int m, int c,
+                                                                     const float *__restrict__ grad_out,
+                                                                     const int *__restrict__ idx,
+                                                                     const float *__restrict__ weight,
+                                                                     float *__restrict__ grad_points) {
+    const int cv = c / VEC;
+    const long total = rows * cv;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
+        const long row = g / cv;
+        const int col = (int)(g - row * cv) * VEC;
+        const long bi = row / n;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const float w = __ldg(weight + row * 3 + t);
+            float *dst = grad_points + (bi * m + __ldg(idx + row * 3 + t)) * c + col;
+            if constexpr (VEC == 4) {
+                float4 v = ldg4(grad_out + row * c + col);
+                v.x = __fmul_rn(v.x, w); v.y = __fmul_rn(v.y, w); v.z = __fmul_rn(v.z, w); v.w = __fmul_rn(v.w, w);
+                atomicAdd(reinterpret_cast<float4 *>(dst), v);
+            } else {
+                atomicAdd(dst, __fmul_rn(__ldg(grad_out + row * c + col), w));
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ================================================================ C ABI
+extern "C" int pasnl_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if ((long)b * m == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(inp && idx && out && n >= 1);
+    return gather_rows((long)b * m, m, n, 3, inp, idx, out, (cudaStream_t)stream);
+}
+
+extern "C" int pasnl_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g,
+                                       void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if ((long)b * n == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(inp_g && (m == 0 || (out_g && idx)));
+    return scatter_rows_add((long)b * m, m > 0 ? m : 1, n, 3, (long)b * n, out_g, idx, inp_g, (cudaStream_t)stream);
+}
+
+extern "C" int pasnl_gather_rows(int b, int n, int c, int m, const float *src, const int *idx, float *out,
+                                 void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0);
+    if ((long)b * m * c == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(src && idx && out && n >= 1);
+    return gather_rows((long)b * m, m, n, c, src, idx, out, (cudaStream_t)stream);
+}
+
+extern "C" int pasnl_gather_rows_grad(int b, int n, int c, int m, const float *out_g, const int *idx, float *src_g,
+                                      void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0);
+    if ((long)b * n * c == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(src_g && (m == 0 || (out_g && idx)));
+    return scatter_rows_add((long)b * m, m > 0 ? m : 1, n, c, (long)b * n, out_g, idx, src_g, (cudaStream_t)stream);
+}
+
+extern "C" int pasnl_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx,
+                                 float *out, void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0 && nsample >= 0);
+    const long rows = (long)b * m * nsample;
+    if (rows * c == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(points && idx && out && n >= 1);
+    return gather_rows(rows, m * nsample, n, c, points, idx, out, (cudaStream_t)stream);
+}
+
+extern "C" int pasnl_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                                      float *grad_points, void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0 && nsample >= 0);
+    if ((long)b * n * c == 0) return PASNL_OK;
+    const long rows = (long)b * m * nsample;
+    PASNL_CHECK_ARG(grad_points && (rows == 0 || (grad_out && idx)));
+    return scatter_rows_add(rows, rows > 0 ? m * nsample : 1, n, c, (long)b * n, grad_out, idx, grad_points,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int pasnl_group_concat(int b, int n, int c, int m, int nsample, const float *xyz, const float *feat,
+                                  const int *idx, int idx_stride, const float *center, float *out, void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0 && nsample >= 0 && idx_stride >= nsample);
+    const long rows = (long)b * m * nsample;
+    if (rows == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(xyz && idx && out && n >= 1 && (c == 0 || feat));
+    const int w = (center ? 3 : 0) + 3 + c;
+    group_concat_kernel<<<grid_for(rows * w), kThreads, 0, (cudaStream_t)stream>>>(rows, m, nsample, n, c, idx_stride,
+                                                                                   xyz, feat, idx, center, out);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_group_concat_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                                       int idx_stride, int has_center, float *grad_xyz, float *grad_feat,
+                                       float *grad_center, void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0 && nsample >= 0 && idx_stride >= nsample);
+    PASNL_CHECK_ARG(grad_xyz || (long)b * n == 0);
+    PASNL_CHECK_ARG(!has_center || grad_center || (long)b * m == 0);
+    PASNL_CHECK_ARG(c == 0 || grad_feat || (long)b * n == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if ((long)b * n > 0) {
+        e = cudaMemsetAsync(grad_xyz, 0, sizeof(float) * (size_t)b * n * 3, st);
+        if (e != cudaSuccess) return (int)e;
+        if (c > 0) {
+            e = cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)b * n * c, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (has_center && (long)b * m > 0) {
+        e = cudaMemsetAsync(grad_center, 0, sizeof(float) * (size_t)b * m * 3, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const long rows = (long)b * m * nsample;
+    if (rows == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(grad_out && idx && n >= 1);
+    const int w = (has_center ? 3 : 0) + 3 + c;
+    group_concat_grad_kernel<<<grid_for(rows * w), kThreads, 0, st>>>(rows, m, nsample, n, c, idx_stride, has_center,
+                                                                      grad_out, idx, grad_xyz, grad_feat, grad_center);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx,
+                                       const float *weight, float *out, void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0);
+    const long rows = (long)b * n;
+    if (rows * c == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(points && idx && weight && out && m >= 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
+        three_interp_kernel<4><<<grid_for(rows * (c / 4)), kThreads, 0, st>>>(rows, n, m, c, points, idx, weight, out);
+    } else {
+        three_interp_kernel<1><<<grid_for(rows * c), kThreads, 0, st>>>(rows, n, m, c, points, idx, weight, out);
+    }
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                                            const float *weight, float *grad_points, void *stream) {
+    PASNL_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && c >= 0);
+    if ((long)b * m * c == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(grad_points);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, st);
+    if (e != cudaSuccess) return (int)e;
+    const long rows = (long)b * n;
+    if (rows == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(grad_out && idx && weight);
+    if (c % 4 == 0 && aligned16(grad_out) && aligned16(grad_points)) {
+        three_interp_grad_kernel<4>
+            <<<grid_for(rows * (c / 4)), kThreads, 0, st>>>(rows, n, m, c, grad_out, idx, weight, grad_points);
+    } else {
+        three_interp_grad_kernel<1>
+            <<<grid_for(rows * c), kThreads, 0, st>>>(rows, n, m, c, grad_out, idx, weight, grad_points);
+    }
+    return pasnl_launch_status();
+}
