@@ -233,9 +233,11 @@ void oracle_group_point_grad(int b, int n, int c, int m, int nsample, const floa
  * (tf_ops/grouping/tf_grouping.py:48-73 -> selection_sort_gpu tf_grouping_g.cu:83-123).
  *   distance = ((dx*dx + dy*dy) + dz*dz) in fp32 without FMA (nanoflann.hpp:341-344; exact search,
  *   eps = 0, knn_.cxx:127); result ascending by distance (KNNResultSet::addPoint, nanoflann.hpp:115-139).
- *   Ties: nanoflann keeps tree-visit order, selection_sort keeps the earliest position (strict '<',
- *   tf_grouping_g.cu:110).  The oracle (and the product) define ties by ascending index, which equals
- *   selection_sort exactly and equals nanoflann whenever no two candidates of a query are equidistant.
+ *   Ties: nanoflann keeps tree-visit order; selection_sort finds the earliest minimum (strict '<',
+ *   tf_grouping_g.cu:110) but then SWAPS it into place, which reorders later equal elements.  Neither order is a
+ *   function of the inputs a caller could rely on, so the oracle (and the product) define ties by ascending index;
+ *   that equals both references whenever no two candidates of a query are equidistant, and always yields the same
+ *   distances position by position.
  * ---------------------------------------------------------------------------------------------- */
 void oracle_knn(int b, int n, int m, int k, const float *xyz1, const float *xyz2, int *idx, float *dist) {
 #pragma omp parallel for num_threads(g_threads) schedule(static)

@@ -1,14 +1,20 @@
-"""Drop-in for utils/pointasnl_util.py (reference): same function names, positional order and return arity.
+"""Drop-in for utils/pointasnl_util.py (reference): same function names, positional order and return arity,
+taking / returning torch CUDA tensors.  TF-specific trailing arguments (is_training, bn_decay, weight_decay,
+scope) are kept; variables live in the active ``tf_util.VariableStore`` under the names TF would give them.
 
-Point-set functions (this file, part 1): knn_query, sampling, grouping  (reference :22-76).
-Layer functions (part 2, below): SampleWeights, AdaptiveSampling, PointNonLocalCell, PointASNLSetAbstraction,
-PointASNLDecodingLayer, get_repulsion_loss -- added with the TF-style variable store in tf_util.
+What runs where: every point-set step (FPS, kNN / ball query, neighbourhood gathers, the Adaptive-Sampling
+attention + re-sampling, the Non-Local attention) is one ``pasnl_*`` CUDA kernel (include/pasnl.h); the 1x1-conv /
+BN / ReLU glue between them is PyTorch (cuBLAS), see tf_util.py.
 """
+import math
+
 import torch
 
-from . import _ops, tf_grouping, tf_sampling  # noqa: F401
+from . import _ops, tf_grouping, tf_interpolate, tf_sampling, tf_util
+from .tf_interpolate import three_interpolate, three_nn  # noqa: F401  (re-exported like the reference module)
 
 
+# ---------------------------------------------------------------------------------------------- point-set functions
 def knn_query(k, support_pts, query_pts):
     """support_pts (B, N1, 3), query_pts (B, N2, 3) -> neighbor_idx (B, N2, k) int32 (reference :22-30).
     The reference leaves the device for a nanoflann kd-tree behind tf.py_func; this is one CUDA kernel with the same
@@ -26,22 +32,245 @@ def sampling(npoint, pts, feature=None):
     return sub, _ops.GatherRows.apply(feature, fps_idx)
 
 
+def _neighbor_idx(K, src_xyz, q_xyz, use_knn, radius):
+    if use_knn:
+        return knn_query(K, src_xyz.detach(), q_xyz.detach())
+    idx, _ = tf_grouping.query_ball_point(radius, K, src_xyz.detach(), q_xyz.detach())
+    return idx
+
+
 def grouping(feature, K, src_xyz, q_xyz, use_xyz=True, use_knn=True, radius=0.2):
     """K neighbours of every q_xyz in src_xyz (reference :51-76) -> grouped_xyz (B, npoint, K, 3),
     grouped_feature (B, npoint, K, [3+]C), idx.
 
     use_knn=True is the path every shipped model takes.  use_knn=False is BROKEN in the reference (it uses `idx`
-    before defining it, :67-71); here it is given the obviously intended meaning (ball query + group_point).
+    before defining it, :67-71); here it has the obviously intended meaning (ball query + group_point).
     idx is returned as the (B, npoint, K) int32 neighbour index (the reference returns the (B, npoint, K, 2)
     [batch, point] pairs tf.gather_nd needs; no caller reads it)."""
-    if use_knn:
-        idx = knn_query(K, src_xyz.detach(), q_xyz.detach())
-    else:
-        idx, _ = tf_grouping.query_ball_point(radius, K, src_xyz.detach(), q_xyz.detach())
+    idx = _neighbor_idx(K, src_xyz, q_xyz, use_knn, radius)
     if use_xyz:
-        grouped_feature = _ops.GroupConcat.apply(src_xyz, feature, idx, None)   # [xyz | feature], one pass
+        grouped_feature = _ops.GroupConcat.apply(src_xyz, feature, idx, None)   # [xyz | feature] in one pass
         grouped_xyz = grouped_feature[..., :3]
     else:
         grouped_xyz = tf_grouping.group_point(src_xyz, idx)
         grouped_feature = tf_grouping.group_point(feature, idx)
     return grouped_xyz, grouped_feature, idx
+
+
+# ---------------------------------------------------------------------------------------------- small MLP helpers
+def weight_net_hidden(xyz, hidden_units, scope, is_training, bn_decay=None, weight_decay=None,
+                      activation_fn=tf_util.relu):
+    """reference :78-88"""
+    with tf_util.variable_scope(scope):
+        net = xyz
+        for i, num_hidden_units in enumerate(hidden_units):
+            net = tf_util.conv2d(net, num_hidden_units, [1, 1], padding="VALID", stride=[1, 1], bn=True,
+                                 is_training=is_training, activation_fn=activation_fn, scope="wconv%d" % i,
+                                 bn_decay=bn_decay, weight_decay=weight_decay)
+    return net
+
+
+def nonlinear_transform(data_in, mlp, scope, is_training, bn_decay=None, weight_decay=None,
+                        activation_fn=tf_util.relu):
+    """reference :90-110 (unused by the shipped models)"""
+    with tf_util.variable_scope(scope):
+        net = data_in
+        n_layers = len(mlp)
+        for i, out_ch in enumerate(mlp[:-1]):
+            net = tf_util.conv2d(net, out_ch, [1, 1], padding="VALID", stride=[1, 1], bn=True, is_training=is_training,
+                                 activation_fn=tf_util.relu, scope="nonlinear%d" % i, bn_decay=bn_decay,
+                                 weight_decay=weight_decay)
+        net = tf_util.conv2d(net, mlp[-1], [1, 1], padding="VALID", stride=[1, 1], bn=False, is_training=is_training,
+                             scope="nonlinear%d" % (n_layers - 1), bn_decay=bn_decay, activation_fn=torch.sigmoid,
+                             weight_decay=weight_decay)
+    return net
+
+
+# ---------------------------------------------------------------------------------------------- Adaptive Sampling
+def _sample_logits(new_point, grouped_xyz, mlps, is_training, bn_decay, weight_decay, scope, bn=True, scaled=True):
+    """Body of SampleWeights up to (excluding) the final softmax over the member axis."""
+    with tf_util.variable_scope(scope):
+        channel = new_point.shape[-1]
+        bottleneck_channel = max(32, channel // 2)
+        normalized_xyz = grouped_xyz - grouped_xyz[:, :, 0:1, :]
+        x = torch.cat([normalized_xyz, new_point], dim=-1)          # (B, S, k, channel + 3)
+        kv = tf_util.conv2d(x, bottleneck_channel * 2, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
+                            is_training=is_training, scope="conv_kv_ds", bn_decay=bn_decay, weight_decay=weight_decay,
+                            activation_fn=None)
+        q = tf_util.conv2d(x, bottleneck_channel, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
+                           is_training=is_training, scope="conv_query_ds", bn_decay=bn_decay,
+                           weight_decay=weight_decay, activation_fn=None)
+        scale = 1.0 / math.sqrt(float(bottleneck_channel)) if scaled else 1.0
+        net = _ops.ASCore.apply(q, kv, scale)                        # softmax(q k^T * scale) v, fused per group
+        for i, c in enumerate(mlps):
+            activation = tf_util.relu if i < len(mlps) - 1 else None
+            net = tf_util.conv2d(net, c, [1, 1], padding="VALID", stride=[1, 1], bn=bn, is_training=is_training,
+                                 scope="mlp2_%d" % i, bn_decay=bn_decay, weight_decay=weight_decay,
+                                 activation_fn=activation)
+    return net
+
+
+def SampleWeights(new_point, grouped_xyz, mlps, is_training, bn_decay, weight_decay, scope, bn=True, scaled=True):
+    """new_point (B, S, k, C), grouped_xyz (B, S, k, 3) -> weights (B, S, k, mlps[-1]), softmax over the k members
+    (reference :112-156)."""
+    return torch.softmax(_sample_logits(new_point, grouped_xyz, mlps, is_training, bn_decay, weight_decay, scope, bn,
+                                        scaled), dim=2)
+
+
+def AdaptiveSampling(group_xyz, group_feature, num_neighbor, is_training, bn_decay, weight_decay, scope, bn):
+    """group_xyz (B, S, K, 3), group_feature (B, S, K, Cg) -> new_xyz (B, S, 3), new_feature (B, S, Cg)
+    (reference :158-173).  The member softmax and both weighted sums are one fused kernel."""
+    with tf_util.variable_scope(scope):
+        num_channel = group_feature.shape[-1]
+        if num_neighbor == 0:
+            return group_xyz[:, :, 0, :], group_feature[:, :, 0, :]
+        shift_group_xyz = group_xyz[:, :, :num_neighbor, :]
+        shift_group_points = group_feature[:, :, :num_neighbor, :]
+        logits = _sample_logits(shift_group_points, shift_group_xyz, [32, 1 + num_channel], is_training, bn_decay,
+                                weight_decay, scope, bn)
+        new_xyz, new_feature = _ops.ASResample.apply(logits, shift_group_xyz, shift_group_points)
+    return new_xyz, new_feature
+
+
+# ---------------------------------------------------------------------------------------------- Non-Local cell
+def PointNonLocalCell(feature, new_point, mlp, is_training, bn_decay, weight_decay, scope, bn=True, scaled=True,
+                      mode="dot"):
+    """feature (B, ndataset, C), new_point (B, npoint, nsample, Cq) -> (B, npoint*nsample..., mlp[-1]) exactly as the
+    reference shapes it (reference :175-219; the SA layer calls it with new_point = (B, 1, npoint, Cq)).
+    The attention map is never materialised: softmax(QK^T)V is one flash-style kernel."""
+    if mode != "dot":
+        raise NotImplementedError("only mode='dot' (the one every shipped model uses) is on the hot path; "
+                                  "mode='concat' materialises a (B, npoint, ndataset, 2D) tensor by construction")
+    with tf_util.variable_scope(scope):
+        bottleneck_channel = mlp[0]
+        batch_size, npoint, nsample, _ = new_point.shape
+        kv = tf_util.conv2d(feature.unsqueeze(2), bottleneck_channel * 2, [1, 1], padding="VALID", stride=[1, 1],
+                            bn=bn, is_training=is_training, scope="conv_kv", bn_decay=bn_decay,
+                            weight_decay=weight_decay, activation_fn=None)
+        q = tf_util.conv2d(new_point, bottleneck_channel, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
+                           is_training=is_training, scope="conv_query", bn_decay=bn_decay, weight_decay=weight_decay,
+                           activation_fn=None)
+        q = q.reshape(batch_size, npoint * nsample, bottleneck_channel)
+        kv = kv.squeeze(2)
+        scale = 1.0 / math.sqrt(float(bottleneck_channel)) if scaled else 1.0
+        d = bottleneck_channel
+        if d % 4:   # the kernel wants a multiple of 4: zero columns change neither q.k nor the kept part of A.v
+            pad = 4 - d % 4
+            q = torch.nn.functional.pad(q, (0, pad))
+            kv = torch.cat([torch.nn.functional.pad(kv[..., :d], (0, pad)),
+                            torch.nn.functional.pad(kv[..., d:], (0, pad))], dim=-1)
+        out = _ops.NLCore.apply(q, kv, scale)[..., :d]
+        out = tf_util.conv2d(out.reshape(batch_size, npoint, nsample, d), mlp[-1], [1, 1], padding="VALID",
+                             stride=[1, 1], bn=bn, is_training=is_training, scope="conv_back_project",
+                             bn_decay=bn_decay, weight_decay=weight_decay)
+        return out.squeeze(1)
+
+
+# ---------------------------------------------------------------------------------------------- SA layer
+def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_decay, weight_decay, scope, bn=True,
+                            use_knn=True, radius=None, as_neighbor=8, NL=True):
+    """xyz (B, ndataset, 3), feature (B, ndataset, C) -> new_xyz (B, npoint, 3), new_points (B, npoint, mlp[-1])
+    (reference :221-292).  Same computation, re-ordered around ONE neighbour search whose index feeds two fused
+    gathers: the first-as_neighbor view for Adaptive Sampling, then [rel xyz | abs xyz | feature] for the local cell."""
+    with tf_util.variable_scope(scope):
+        batch_size, num_points, num_channel = feature.shape
+        sampled = num_points != npoint
+        if sampled:
+            new_xyz, new_feature = sampling(npoint, xyz, feature)        # FPS + row gathers
+        else:
+            new_xyz, new_feature = xyz, feature
+        idx = _neighbor_idx(nsample, xyz, new_xyz, use_knn, radius)       # (B, npoint, nsample) int32
+        nl_channel = mlp[-1]
+
+        if sampled:                                                        # Adaptive Sampling (reference :246-247)
+            k_as = as_neighbor if as_neighbor > 0 else 1
+            group_as = _ops.GroupConcat.apply(xyz, feature, idx[:, :, :k_as], None)   # (B, S, k, 3 + C) = [xyz | feat]
+            new_xyz, new_feature = AdaptiveSampling(group_as[..., :3], group_as, as_neighbor, is_training, bn_decay,
+                                                    weight_decay, scope, bn)
+        # translation normalisation + concat (reference :248-249): [xyz_j - new_xyz | xyz_j | feature_j]
+        new_point = _ops.GroupConcat.apply(xyz, feature, idx, new_xyz)
+        grouped_xyz = new_point[..., :3]
+
+        if NL:                                                             # reference :252-256
+            new_nonlocal_point = PointNonLocalCell(feature, new_feature.unsqueeze(1),
+                                                   [max(32, num_channel // 2), nl_channel], is_training, bn_decay,
+                                                   weight_decay, scope, bn)
+        # skip connection (reference :258-262)
+        skip_spatial = new_point.amax(dim=2)
+        skip_spatial = tf_util.conv1d(skip_spatial, mlp[-1], 1, padding="VALID", stride=1, bn=bn,
+                                      is_training=is_training, scope="skip", bn_decay=bn_decay,
+                                      weight_decay=weight_decay)
+        # point local cell (reference :264-280)
+        for i, num_out_channel in enumerate(mlp):
+            if i != len(mlp) - 1:
+                new_point = tf_util.conv2d(new_point, num_out_channel, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
+                                           is_training=is_training, scope="conv%d" % i, bn_decay=bn_decay,
+                                           weight_decay=weight_decay)
+        weight = weight_net_hidden(grouped_xyz, [32], scope="weight_net", is_training=is_training, bn_decay=bn_decay,
+                                   weight_decay=weight_decay)
+        new_point = torch.matmul(new_point.transpose(2, 3), weight)        # (B, S, C', K) x (B, S, K, 32)
+        new_point = tf_util.conv2d(new_point, mlp[-1], [1, new_point.shape[2]], padding="VALID", stride=[1, 1],
+                                   bn=bn, is_training=is_training, scope="after_conv", bn_decay=bn_decay,
+                                   weight_decay=weight_decay)
+        new_point = new_point.squeeze(2)
+        new_point = new_point + skip_spatial
+        if NL:
+            new_point = new_point + new_nonlocal_point
+        # feature fusion (reference :287-290)
+        new_point = tf_util.conv1d(new_point, mlp[-1], 1, padding="VALID", stride=1, bn=bn, is_training=is_training,
+                                   scope="aggregation", bn_decay=bn_decay, weight_decay=weight_decay)
+        return new_xyz, new_point
+
+
+# ---------------------------------------------------------------------------------------------- decoding layer
+def PointASNLDecodingLayer(xyz1, xyz2, points1, points2, nsample, mlp, is_training, bn_decay, weight_decay, scope,
+                           bn=True, use_xyz=True, use_knn=True, radius=None, dilate_rate=1, mode="concat", NL=False):
+    """xyz1 (B, n1, 3) dense, xyz2 (B, n2, 3) sparse, points1 (B, n1, c1), points2 (B, n2, c2) -> (B, n1, mlp[-1])
+    (reference :294-351; used by models/pointasnl_sem_seg.py)."""
+    with tf_util.variable_scope(scope):
+        num_channel = points2.shape[-1]
+        dist, idx = three_nn(xyz1.detach(), xyz2.detach())
+        dist = torch.clamp(dist, min=1e-10)
+        norm = (1.0 / dist).sum(dim=2, keepdim=True)
+        weight = (1.0 / dist) / norm
+        if NL:
+            new_nonlocal_point = PointNonLocalCell(points1, points2.unsqueeze(1), [max(32, num_channel), num_channel],
+                                                   is_training, bn_decay, weight_decay, scope, bn, mode=mode)
+            points2 = points2 + new_nonlocal_point
+        interpolated_points = three_interpolate(points2, idx, weight)
+        grouped_xyz, grouped_feature, _ = grouping(interpolated_points, nsample, xyz1, xyz1, use_xyz=use_xyz,
+                                                   use_knn=use_knn, radius=radius)
+        grouped_xyz = grouped_xyz - xyz1.unsqueeze(2)
+        weight = weight_net_hidden(grouped_xyz, [32], scope="decode_weight_net", is_training=is_training,
+                                   bn_decay=bn_decay, weight_decay=weight_decay)
+        new_points = torch.matmul(grouped_feature.transpose(2, 3), weight)
+        new_points = tf_util.conv2d(new_points, mlp[0], [1, new_points.shape[2]], padding="VALID", stride=[1, 1],
+                                    bn=bn, is_training=is_training, scope="decode_after_conv", bn_decay=bn_decay,
+                                    weight_decay=weight_decay)
+        if points1 is not None:
+            new_points1 = torch.cat([new_points, points1.unsqueeze(2)], dim=-1)
+        else:
+            new_points1 = new_points
+        for i, num_out_channel in enumerate(mlp):
+            if i != 0:
+                new_points1 = tf_util.conv2d(new_points1, num_out_channel, [1, 1], padding="VALID", stride=[1, 1],
+                                             bn=bn, is_training=is_training, scope="conv_%d" % i, bn_decay=bn_decay,
+                                             weight_decay=weight_decay)
+        return new_points1.squeeze(2)
+
+
+# ---------------------------------------------------------------------------------------------- repulsion loss
+def get_repulsion_loss(pred, nsample=20, radius=0.07):
+    """pred (B, npoint, 3) -> scalar (reference :361-378): ball query + group on (pred, pred), the 4 smallest
+    non-self squared distances per point, mean(radius - d * exp(-d^2 / h^2)), h = 0.03."""
+    idx, _pts_cnt = tf_grouping.query_ball_point(radius, nsample, pred.detach(), pred.detach())
+    grouped_pred = tf_grouping.group_point(pred, idx)
+    grouped_pred = grouped_pred - pred.unsqueeze(2)
+    h = 0.03
+    dist_square = (grouped_pred ** 2).sum(dim=-1)
+    neg, _ = torch.topk(-dist_square, 5, dim=-1)
+    dist_square = -neg[:, :, 1:]
+    dist_square = torch.clamp(dist_square, min=1e-12)
+    dist = torch.sqrt(dist_square)
+    weight = torch.exp(-dist_square / h ** 2)
+    return torch.mean(radius - dist * weight)

@@ -20,13 +20,15 @@ def knn_point(k, xyz1, xyz2):
     """k int, xyz1 (b, ndataset, 3) support, xyz2 (b, npoint, 3) queries -> val (b, npoint, k) squared L2
     distances ascending, idx (b, npoint, k) int32 (reference tf_grouping.py:48-73).  No gradient.
     The reference materialises the (b, npoint, ndataset) distance matrix and selection-sorts it; here it is one
-    tiled kernel with the same (distance, earliest index) order."""
+    tiled kernel: same distances position by position; equidistant neighbours come in ascending index order
+    (the reference's swap-based selection sort leaves them in a swap-history-dependent order)."""
     return _ops.knn(k, xyz1, xyz2, return_dist=True)
 
 
 def select_top_k(k, dist):
     """dist (b, m, n) -> idx (b, m, n) int32, dist_out (b, m, n): the first k entries of each row are the k smallest
-    in ascending order with the earliest index first on ties, as selection_sort_gpu produces them
+    in ascending order (ascending index among equal distances; selection_sort_gpu's swaps leave ties in a
+    history-dependent order)
     (reference tf_grouping.py:22-32, tf_grouping_g.cu:83-123); the remaining n-k entries follow in ascending order
     too (the reference leaves them as an unspecified permutation -- only the first k are documented as useful).
     Not used by the shipped models; implemented with a stable device sort."""

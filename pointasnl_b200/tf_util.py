@@ -1,0 +1,245 @@
+"""Host-side mirror of the reference's utils/tf_util.py for the callers of the hot path.
+
+The reference builds its dense glue (1x1 conv + bias + batch norm + activation, fully connected, dropout) as TF1
+graph ops that create variables by *scope name* (tf.variable_scope / tf.get_variable).  To keep
+``pointasnl_util.PointASNLSetAbstraction(xyz, feature, ..., scope, ...)`` and friends drop-in at the signature
+level, this module reproduces exactly that: a ``VariableStore`` (an nn.Module) in which variables are created on
+first use under the same nested scope names TF would give them (``layer1/layer1/conv_kv/weights`` ...), and reused
+afterwards (AUTO_REUSE).  Dense math itself is plain PyTorch (cuBLAS): it is NOT part of the hot path this repo
+re-implements -- only the call semantics matter: bias -> batch norm -> activation order
+(reference tf_util.py:170-185), NHWC layout, xavier init, BN eps 1e-3 with biased batch variance (:512-531).
+
+Documented deviations: moving_variance is updated with torch's unbiased batch variance (TF's non-fused
+contrib batch_norm uses the biased one); this affects inference-mode statistics only, never a training step.
+"""
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as F
+
+relu = torch.relu
+
+
+def leaky_relu(x):
+    return F.leaky_relu(x, 0.2)  # tf.nn.leaky_relu default alpha
+
+
+class VariableStore(torch.nn.Module):
+    """TF1-style variable store: ``get_variable`` creates a Parameter (or buffer) under the current scope path on
+    first use and returns the existing one afterwards."""
+
+    def __init__(self, device="cuda", seed=0):
+        super().__init__()
+        self.device = torch.device(device)
+        self._scope = []
+        self._gen = torch.Generator(device="cpu")
+        self._gen.manual_seed(seed)
+        self.weight_decay = {}   # variable name -> wd  (tf.add_to_collection('losses', wd * l2_loss(var)))
+        self._names = {}         # TF name -> attribute key
+
+    # -- scopes
+    @contextlib.contextmanager
+    def variable_scope(self, name):
+        self._scope.append(str(name))
+        try:
+            yield
+        finally:
+            self._scope.pop()
+
+    def full_name(self, name):
+        return "/".join(self._scope + [name])
+
+    @staticmethod
+    def _key(full):
+        return full.replace("/", "__").replace(".", "_")
+
+    # -- variables
+    def get_variable(self, name, shape, init, trainable=True, wd=None):
+        full = self.full_name(name)
+        key = self._key(full)
+        if full in self._names:
+            v = getattr(self, key)
+            if tuple(v.shape) != tuple(shape):
+                raise ValueError(f"variable {full} exists with shape {tuple(v.shape)}, requested {tuple(shape)}")
+            return v
+        value = init(tuple(shape), self._gen).to(self.device)
+        if trainable:
+            self.register_parameter(key, torch.nn.Parameter(value))
+        else:
+            self.register_buffer(key, value)
+        self._names[full] = key
+        if wd is not None:
+            self.weight_decay[full] = float(wd)
+        return getattr(self, key)
+
+    def variables(self):
+        """TF name -> tensor, for every variable created so far."""
+        return {full: getattr(self, key) for full, key in self._names.items()}
+
+    def load_variables(self, values):
+        with torch.no_grad():
+            for full, val in values.items():
+                getattr(self, self._names[full]).copy_(torch.as_tensor(val).to(self.device))
+
+    def regularization_loss(self):
+        """sum of wd * l2_loss(var) over variables created with weight decay (tf.nn.l2_loss = sum(v^2)/2)."""
+        terms = [wd * 0.5 * (getattr(self, self._names[n]) ** 2).sum() for n, wd in self.weight_decay.items()]
+        return torch.stack(terms).sum() if terms else torch.zeros((), device=self.device)
+
+
+_default_store = None
+
+
+def get_default_store():
+    if _default_store is None:
+        raise RuntimeError("no VariableStore is active: wrap the model call in `with store.as_default():`")
+    return _default_store
+
+
+@contextlib.contextmanager
+def as_default(store):
+    global _default_store
+    prev = _default_store
+    _default_store = store
+    try:
+        yield store
+    finally:
+        _default_store = prev
+
+
+VariableStore.as_default = lambda self: as_default(self)
+
+
+def variable_scope(name):
+    return get_default_store().variable_scope(name)
+
+
+# ---------------------------------------------------------------- initialisers
+def xavier_init(fan_in, fan_out):
+    limit = math.sqrt(6.0 / (fan_in + fan_out))  # tf.contrib.layers.xavier_initializer (uniform)
+
+    def init(shape, gen):
+        return (torch.rand(shape, generator=gen) * 2.0 - 1.0) * limit
+    return init
+
+
+def truncated_normal_init(stddev):
+    def init(shape, gen):
+        t = torch.empty(shape)
+        torch.nn.init.trunc_normal_(t, 0.0, stddev, -2 * stddev, 2 * stddev, generator=gen)
+        return t
+    return init
+
+
+def constant_init(value):
+    def init(shape, gen):
+        return torch.full(shape, float(value))
+    return init
+
+
+def _weights(shape, fan_in, fan_out, use_xavier, stddev, wd):
+    init = xavier_init(fan_in, fan_out) if use_xavier else truncated_normal_init(stddev)
+    return get_default_store().get_variable("weights", shape, init, wd=wd)
+
+
+# ---------------------------------------------------------------- batch norm
+def batch_norm_template(inputs, is_training, scope, moments_dims_unused, bn_decay, data_format="NHWC"):
+    """tf.contrib.layers.batch_norm(center=True, scale=True, decay=bn_decay, updates_collections=None), eps 1e-3
+    (reference tf_util.py:512-531): statistics over every axis but the channel one."""
+    if data_format != "NHWC":
+        raise NotImplementedError("only the NHWC layout the hot path uses is mirrored")
+    decay = 0.9 if bn_decay is None else float(bn_decay)
+    store = get_default_store()
+    c = inputs.shape[-1]
+    with store.variable_scope(scope):
+        beta = store.get_variable("beta", (c,), constant_init(0.0))
+        gamma = store.get_variable("gamma", (c,), constant_init(1.0))
+        mean = store.get_variable("moving_mean", (c,), constant_init(0.0), trainable=False)
+        var = store.get_variable("moving_variance", (c,), constant_init(1.0), trainable=False)
+    x2 = inputs.reshape(-1, c)
+    y = F.batch_norm(x2, mean, var, gamma, beta, bool(is_training), 1.0 - decay, 1e-3)
+    return y.reshape(inputs.shape)
+
+
+def batch_norm_for_fc(inputs, is_training, bn_decay, scope):
+    return batch_norm_template(inputs, is_training, scope, [0], bn_decay)
+
+
+def batch_norm_for_conv1d(inputs, is_training, bn_decay, scope, data_format="NHWC"):
+    return batch_norm_template(inputs, is_training, scope, [0, 1], bn_decay, data_format)
+
+
+def batch_norm_for_conv2d(inputs, is_training, bn_decay, scope, data_format="NHWC"):
+    return batch_norm_template(inputs, is_training, scope, [0, 1, 2], bn_decay, data_format)
+
+
+# ---------------------------------------------------------------- layers (signatures as in the reference)
+def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="SAME", data_format="NHWC",
+           use_xavier=True, stddev=1e-3, weight_decay=None, activation_fn=relu, bn=False, bn_decay=None,
+           is_training=None):
+    """inputs (B, L, C).  Only kernel_size 1 / stride 1 occurs on the hot path (reference tf_util.py:60-115)."""
+    if kernel_size != 1 or stride != 1 or data_format != "NHWC":
+        raise NotImplementedError("conv1d mirror supports kernel_size=1, stride=1, NHWC (all the hot path uses)")
+    store = get_default_store()
+    cin = inputs.shape[-1]
+    with store.variable_scope(scope):
+        w = _weights((1, cin, num_output_channels), cin, num_output_channels, use_xavier, stddev, weight_decay)
+        b = store.get_variable("biases", (num_output_channels,), constant_init(0.0))
+        out = torch.matmul(inputs, w[0]) + b
+        if bn:
+            out = batch_norm_for_conv1d(out, is_training, bn_decay, "bn", data_format)
+        if activation_fn is not None:
+            out = activation_fn(out)
+    return out
+
+
+def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], padding="SAME", data_format="NHWC",
+           use_xavier=True, stddev=1e-3, weight_decay=None, activation_fn=relu, bn=False, bn_decay=None,
+           is_training=None):
+    """inputs (B, H, W, C).  Supported kernels: [1,1], and [1,W] with padding='VALID' (the PointConv-style
+    `after_conv`, reference pointasnl_util.py:275-278), which is a matmul over the flattened (W, C) axes
+    (reference tf_util.py:120-185)."""
+    kh, kw = kernel_size
+    if kh != 1 or list(stride) != [1, 1] or data_format != "NHWC":
+        raise NotImplementedError("conv2d mirror supports kernel height 1, stride 1, NHWC")
+    store = get_default_store()
+    b_, h, wdt, cin = inputs.shape
+    with store.variable_scope(scope):
+        w = _weights((kh, kw, cin, num_output_channels), kh * kw * cin, kh * kw * num_output_channels, use_xavier,
+                     stddev, weight_decay)
+        bias = store.get_variable("biases", (num_output_channels,), constant_init(0.0))
+        if kw == 1:
+            out = torch.matmul(inputs, w[0, 0]) + bias
+        elif kw == wdt and padding == "VALID":
+            out = torch.matmul(inputs.reshape(b_, h, 1, wdt * cin), w.reshape(kw * cin, num_output_channels)) + bias
+        else:
+            raise NotImplementedError(f"conv2d mirror: kernel [1,{kw}] on width {wdt} with padding {padding}")
+        if bn:
+            out = batch_norm_for_conv2d(out, is_training, bn_decay, "bn", data_format)
+        if activation_fn is not None:
+            out = activation_fn(out)
+    return out
+
+
+def fully_connected(inputs, num_outputs, scope, use_xavier=True, stddev=1e-3, weight_decay=None, activation_fn=relu,
+                    bn=False, bn_decay=None, is_training=None):
+    """inputs (B, N) (reference tf_util.py:318-355)."""
+    store = get_default_store()
+    cin = inputs.shape[-1]
+    with store.variable_scope(scope):
+        w = _weights((cin, num_outputs), cin, num_outputs, use_xavier, stddev, weight_decay)
+        b = store.get_variable("biases", (num_outputs,), constant_init(0.0))
+        out = torch.matmul(inputs, w) + b
+        if bn:
+            out = batch_norm_for_fc(out, is_training, bn_decay, "bn")
+        if activation_fn is not None:
+            out = activation_fn(out)
+    return out
+
+
+def dropout(inputs, is_training, scope, keep_prob=0.5, noise_shape=None):
+    """tf.nn.dropout(inputs, keep_prob) when training (reference tf_util.py:590-615)."""
+    if noise_shape is not None:
+        raise NotImplementedError("noise_shape is not used on the hot path")
+    return F.dropout(inputs, p=1.0 - keep_prob, training=bool(is_training))
