@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- point-clouds/s for one training step (forward + loss + backward + gradient all-reduce + Adam) of
+pointasnl_cls on ModelNet40-shaped synthetic input, B=32 clouds of N=1024 points per GPU (BASELINE.json configs[1];
+--AS gives configs[2]; --workload seg gives configs[3] shape).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU under torchrun
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the box's HOST cores
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract: value = whole-job clouds/s with inputs resident in
+HBM; e2e = the same step fed from pinned host memory with the loss read back every step; roofline = the dominant
+pasnl kernel of the step against the measured B200 peaks; cpu_baseline = the CPU restatement timed on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "point-clouds/sec fwd+bwd ModelNet40 B=32 N=1024"
+UNIT = "clouds/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cls", choices=["cls", "seg"])
+    ap.add_argument("--AS", action="store_true", help="adaptive sampling on (BASELINE configs[2])")
+    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default 32 cls / 4 seg)")
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graphs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-report", default=None, help="write the per-kernel table (JSON) to this path")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ data
+def make_batch(workload, batch, points, seed):
+    from tests import synth
+    if workload == "cls":
+        pc, labels = synth.modelnet_batch(batch, points, seed)
+        return pc, labels, None
+    pts, labels, smpw = synth.scannet_batch(batch, points, seed)
+    return pts, labels, smpw
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ per-kernel model
+def algorithmic_work(name, a):
+    """(bytes, flops, bound) of one launch from its integer arguments (stated in DESIGN.md)."""
+    if name == "pasnl_fps":
+        b, n, m = a[0:3]
+        return 12 * b * n + 4 * b * m, 10 * b * m * n, "latency"
+    if name == "pasnl_knn":
+        b, n, m, k = a[0:4]
+        return 12 * b * (n + m) + 4 * b * m * k, 8 * b * m * n, "fp32"
+    if name == "pasnl_ball_query":
+        b, n, m, _r, k = a[0:5]
+        return 12 * b * (n + m) + 4 * b * m * (k + 1), 9 * b * m * n, "fp32"
+    if name in ("pasnl_gather_rows", "pasnl_gather_rows_grad"):
+        b, n, c, m = a[0:4]
+        return 4 * b * m + 4 * b * n * c + 4 * b * m * c, 0, "hbm"
+    if name in ("pasnl_gather_point", "pasnl_gather_point_grad"):
+        b, n, m = a[0:3]
+        return 4 * b * m + 12 * b * n + 12 * b * m, 0, "hbm"
+    if name in ("pasnl_group_point", "pasnl_group_point_grad"):
+        b, n, c, m, ns = a[0:5]
+        return 4 * b * m * ns + 4 * b * n * c + 4 * b * m * ns * c, 0, "hbm"
+    if name == "pasnl_group_concat":
+        b, n, c, m, ns = a[0:5]
+        w = (3 if a[9] else 0) + 3 + c
+        return 4 * b * m * ns + 4 * b * n * (3 + c) + (12 * b * m if a[9] else 0) + 4 * b * m * ns * w, 0, "hbm"
+    if name == "pasnl_group_concat_grad":
+        b, n, c, m, ns = a[0:5]
+        w = (3 if a[8] else 0) + 3 + c
+        return 4 * b * m * ns + 4 * b * n * (3 + c) + (12 * b * m if a[8] else 0) + 4 * b * m * ns * w, b * m * ns * w, "hbm"
+    if name == "pasnl_three_nn":
+        b, n, m = a[0:3]
+        return 12 * b * (n + m) + 24 * b * n, 8 * b * n * m, "fp32"
+    if name in ("pasnl_three_interpolate", "pasnl_three_interpolate_grad"):
+        if name == "pasnl_three_interpolate":
+            b, m, c, n = a[0:4]
+        else:
+            b, n, c, m = a[0:4]
+        return 4 * b * m * c + 24 * b * n + 4 * b * n * c, 5 * b * n * c, "hbm"
+    if name == "pasnl_as_core_fwd":
+        g, k, d = a[0:3]
+        return 16 * g * k * d + 4 * g * k * k, 4 * g * k * k * d, "hbm"
+    if name == "pasnl_as_core_bwd":
+        g, k, d = a[0:3]
+        return 28 * g * k * d + 4 * g * k * k, 10 * g * k * k * d, "hbm"
+    if name == "pasnl_as_resample_fwd":
+        g, k, cg = a[0:3]
+        return 4 * g * k * (1 + cg) * 2 + 12 * g * k + 4 * g * k * cg + 4 * g * (3 + cg), 4 * g * k * (1 + cg), "hbm"
+    if name == "pasnl_as_resample_bwd":
+        g, k, cg = a[0:3]
+        return 4 * g * k * (1 + cg) * 2 + 24 * g * k + 8 * g * k * cg + 4 * g * (3 + cg), 6 * g * k * (1 + cg), "hbm"
+    if name == "pasnl_nl_core_fwd":
+        b, s, n, d = a[0:4]
+        return 4 * b * (2 * s * d + 2 * n * d) + 4 * b * s, 4 * b * s * n * d, "tensor"
+    if name == "pasnl_nl_core_bwd":
+        b, s, n, d = a[0:4]
+        return 4 * b * (4 * s * d + 4 * n * d) + 8 * b * s, 10 * b * s * n * d, "tensor"
+    return 0, 0, "hbm"
+
+
+class KernelProfiler:
+    """CUDA events around every pasnl_* call (on torch's current stream, which is the stream the library launches
+    on).  Used in a separate pass so that the headline timing carries no instrumentation."""
+
+    def __init__(self):
+        self.records = []
+        self._start = None
+
+    def before(self, name, args):
+        self._start = torch.cuda.Event(enable_timing=True)
+        self._start.record()
+
+    def after(self, name, args):
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        ints = tuple(x if isinstance(x, (int, float)) else (None if x is None else 1) for x in args)
+        self.records.append((name, ints, self._start, end))
+
+    def table(self, steps):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, ints, s, e in self.records:
+            ms = s.elapsed_time(e)
+            by, fl, bound = algorithmic_work(name, ints)
+            dims = []
+            for v in ints:      # leading shape arguments; stop at the first device pointer
+                if v is None or (isinstance(v, int) and abs(v) >= 2 ** 32):
+                    break
+                dims.append(round(v, 6) if isinstance(v, float) else int(v))
+            key = (name,) + tuple(dims)
+            r = agg.setdefault(key, {"name": name, "dims": list(key[1:]), "calls": 0, "ms": 0.0, "bytes": by,
+                                     "flops": fl, "bound": bound})
+            r["calls"] += 1
+            r["ms"] += ms
+        rows = []
+        for r in agg.values():
+            avg = r["ms"] / r["calls"]
+            rows.append({**r, "avg_us": 1e3 * avg, "ms_per_step": r["ms"] / steps,
+                         "gbs": r["bytes"] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0,
+                         "tflops": r["flops"] / (avg * 1e-3) / 1e12 if avg > 0 else 0.0})
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        return rows
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_cpu_reference(args, batch, points, steps, warmup, threads=None):
+    """The reference's algorithm on host cores: oracle/model_ref.py (line-by-line restatement of the TF graph code,
+    reference-native nanoflann kNN / three_nn / three_interpolate where oracle/_ref has them, C restatement for the
+    GPU-only ops).  Returns (clouds_per_s, ms_per_step, cores, description)."""
+    from oracle import cref, model_ref, refnative
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cref.set_threads(cores)
+    pc, labels, smpw = make_batch(args.workload, batch, points, 1)
+    x = torch.from_numpy(pc)
+    y = torch.from_numpy(labels)
+    # variables are created lazily by the oracle with the reference's initialisers (same architecture, random init)
+    r = model_ref.Ref(None, dtype=torch.float32, dropout=True, native_knn=True, native_interp=True)
+
+    def fwd():
+        if args.workload == "cls":
+            return model_ref.cls_forward(r, x, y, use_normal=True, adaptive_sample=args.AS)[1]
+        return model_ref.seg_forward(r, x, 21, y, torch.from_numpy(smpw), feature_channel=3)[1]
+
+    with torch.no_grad():
+        fwd()          # instantiate the variables
+    params = [v for v in r.v.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3)
+
+    def one_step():
+        opt.zero_grad(set_to_none=True)
+        total = fwd()
+        total.backward()
+        opt.step()
+        return float(total)
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    kind = "reference" if refnative.available("ref_knn.so") else "port"
+    return batch * steps / dt, 1e3 * dt / steps, cores, kind
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    batch = args.batch or (32 if args.workload == "cls" else 4)
+    points = args.points or (1024 if args.workload == "cls" else 10240)
+    workload_name = ("pointasnl_cls" + ("+AS" if args.AS else "") if args.workload == "cls" else "pointasnl_sem_seg_res") \
+        + f" B={batch} N={points} per GPU, synthetic"
+    config = {"workload": workload_name, "step": "forward + loss + backward + grad all-reduce + Adam",
+              "parallelism": f"dp{world}", "global_batch": batch * world}
+
+    # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample: a few full steps of the same workload on all host cores
+        steps = max(1, min(args.steps, 3))
+        warm = 1
+        val, ms, cores, kind = run_cpu_reference(args, batch, points, steps, warm)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                                 "sample": f"{steps} full steps of {batch} clouds (after {warm} warm-up), torch CPU + "
+                                           "reference-native nanoflann kNN; FPS from the C restatement (the reference "
+                                           "has no CPU FPS)"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------- this repo's CUDA path
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from pointasnl_b200 import _lib, dp
+    from pointasnl_b200.callers.train_step import TrainStep
+
+    pc, labels, smpw = make_batch(args.workload, batch, points, 1 if world == 1 else 1000 + rank)
+    h_pc = torch.from_numpy(pc).pin_memory()
+    h_lab = torch.from_numpy(labels).pin_memory()
+    h_w = torch.from_numpy(smpw).pin_memory() if smpw is not None else None
+    ts = TrainStep(args.workload, batch, points, dev, adaptive_sample=args.AS, use_graph=not args.no_graph, seed=0)
+    ts.set_inputs(h_pc, h_lab, h_w)
+    torch.cuda.synchronize()
+    if not args.no_graph:
+        ts.capture(warmup=3)
+    for _ in range(max(args.warmup, 3)):
+        ts.step()
+    torch.cuda.synchronize()
+    launches_per_step = None
+    if args.no_graph:
+        c0 = _lib.launch_count
+        ts.step()
+        launches_per_step = _lib.launch_count - c0
+    else:
+        launches_per_step = ts.launches_per_step
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        for i in range(args.steps):
+            flush.zero_()
+            starts[i].record()
+            ts.step()
+            ends[i].record()
+        barrier()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = dp.max_over_ranks(sum(step_ms), dev)
+    value = batch * world * args.steps / (total_ms * 1e-3)
+
+    # ---- timed region 2: end to end from pinned host memory, loss read back every step
+    e2e_t = []
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ts.set_inputs(h_pc, h_lab, h_w)
+        loss_host = float(ts.step().item())     # D2H read of the step's result
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    assert np.isfinite(loss_host)
+    e2e_total = dp.max_over_ranks(sum(e2e_t), dev)
+    e2e_value = batch * world * args.steps / e2e_total
+    h2d = h_pc.numel() * 4 + h_lab.numel() * 8 + (h_w.numel() * 4 if h_w is not None else 0)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- per-kernel pass (eager, CUDA events around each pasnl launch) -> roofline of the dominant kernel
+    peaks = load_peaks()
+    prof_steps = min(args.steps, 5)
+    ts_prof = ts if args.no_graph else None
+    if ts_prof is None:
+        ts_prof = TrainStep(args.workload, batch, points, dev, adaptive_sample=args.AS, use_graph=False, seed=0)
+        ts_prof.bucket.all_reduce_mean = lambda *a, **k: None   # rank-0 only pass: no collective
+        ts_prof.set_inputs(h_pc, h_lab, h_w)
+        for _ in range(2):
+            ts_prof.step()
+    prof = KernelProfiler()
+    torch.cuda.synchronize()
+    _lib.profiler = prof
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(prof_steps):
+        ts_prof.step()
+    ev1.record()
+    _lib.profiler = None
+    rows = prof.table(prof_steps)
+    eager_ms = ev0.elapsed_time(ev1) / prof_steps
+    ours_ms = sum(r["ms_per_step"] for r in rows)
+    top = rows[0]
+    if top["bound"] == "tensor":
+        roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": top["tflops"] / peaks["bf16_tflops"]}
+    else:
+        roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": top["gbs"] / peaks["hbm_gbs"]}
+    roof.update({"traffic": None, "kernel": top["name"], "dims": top["dims"], "avg_us": top["avg_us"],
+                 "native_bound": top["bound"], "peak_source": peaks["src"],
+                 "timing": f"CUDA events around each launch, eager pass of {prof_steps} steps",
+                 "pasnl_share_of_step": ours_ms / eager_ms if eager_ms > 0 else None})
+    if args.kernel_report:
+        os.makedirs(os.path.dirname(os.path.abspath(args.kernel_report)), exist_ok=True)
+        json.dump({"eager_ms_per_step": eager_ms, "pasnl_ms_per_step": ours_ms, "peaks": peaks, "kernels": rows},
+                  open(args.kernel_report, "w"), indent=1)
+
+    # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, ms, cores, kind = run_cpu_reference(args, batch, points, steps=1, warmup=1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": f"1 full step of {batch} clouds after 1 warm-up ({ms:.0f} ms), torch CPU + reference-native "
+                             "nanoflann kNN; FPS from the C restatement"}
+        except Exception as e:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {**config, "l2": "flushed (256 MiB memset) before every timed step, outside the event pair",
+                       "launch": "eager" if args.no_graph else "CUDA graphs (fwd+bwd, Adam) around one NCCL all-reduce"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,7 +52,14 @@ class PasnlError(RuntimeError):
 
 
 _lib = None
-launch_count = 0  # number of pasnl_* compute entry points invoked (bench.py reports it as gpu_launches)
+launch_count = 0   # CUDA kernels launched by pasnl_* entry points so far (bench.py reports the delta as gpu_launches)
+profiler = None    # optional object with before(name, args) / after(name, args), set by bench.py's per-kernel pass
+
+# kernels (incl. memset nodes) each entry point enqueues; everything not listed launches exactly one kernel
+KERNELS_PER_CALL = {
+    "pasnl_gather_point_grad": 2, "pasnl_gather_rows_grad": 2, "pasnl_group_point_grad": 2,
+    "pasnl_three_interpolate_grad": 2, "pasnl_group_concat_grad": 4, "pasnl_nl_core_bwd": 3,
+}
 
 
 def load():
@@ -91,8 +98,14 @@ def check(code, what):
 def call(name, *args):
     """Invoke a compute entry point and raise on a non-zero return code."""
     global launch_count
-    launch_count += 1
-    check(getattr(load(), name)(*args), name)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    fn = getattr(load(), name)
+    if profiler is None:
+        check(fn(*args), name)
+    else:
+        profiler.before(name, args)
+        check(fn(*args), name)
+        profiler.after(name, args)
 
 
 def ptr(t):

@@ -1,0 +1,94 @@
+"""One training step of a caller model (forward + loss + backward + gradient all-reduce + Adam), eager or captured
+into a CUDA graph.  This is the call bench.py times and what a user of the drop-in API would write by hand."""
+import torch
+
+from .. import tf_util
+from ..dp import FlatGradBucket
+from . import pointasnl_cls, pointasnl_sem_seg_res
+
+
+class TrainStep:
+    def __init__(self, model="cls", batch_size=32, num_point=1024, device="cuda", adaptive_sample=False,
+                 num_class=None, feature_channel=3, lr=1e-3, seed=0, use_graph=False):
+        self.kind = model
+        self.device = torch.device(device)
+        self.batch_size, self.num_point = batch_size, num_point
+        self.adaptive_sample = adaptive_sample
+        self.feature_channel = feature_channel
+        self.num_class = num_class or (40 if model == "cls" else 21)
+        self.store = tf_util.VariableStore(self.device, seed=seed)
+        c = 6 if model == "cls" else 3 + feature_channel
+        # static device buffers: the step reads these (required for graph replay, harmless in eager mode)
+        self.points = torch.zeros((batch_size, num_point, c), device=self.device)
+        if model == "cls":
+            self.labels = torch.zeros((batch_size,), dtype=torch.int64, device=self.device)
+            self.smpw = None
+        else:
+            self.labels = torch.zeros((batch_size, num_point), dtype=torch.int64, device=self.device)
+            self.smpw = torch.ones((batch_size, num_point), device=self.device)
+        self.loss = torch.zeros((), device=self.device)
+        with torch.no_grad():   # materialise every variable (TF would do this at graph-construction time)
+            self._forward()
+        self.bucket = FlatGradBucket(self.store.parameters())
+        self.opt = torch.optim.Adam(self.bucket.params, lr=lr, capturable=use_graph)
+        self.graph = None
+        self.use_graph = use_graph
+        self.launches_per_step = None
+
+    def _forward(self):
+        with self.store.as_default():
+            if self.kind == "cls":
+                pred, end_points = pointasnl_cls.get_model(self.points, True, use_normal=True,
+                                                           adaptive_sample=self.adaptive_sample,
+                                                           num_class=self.num_class)
+                return pointasnl_cls.get_loss(pred, self.labels, end_points)
+            pred, end_points = pointasnl_sem_seg_res.get_model(self.points, True, self.num_class,
+                                                               feature_channel=self.feature_channel)
+            return pointasnl_sem_seg_res.get_loss(pred, self.labels, end_points, self.smpw)
+
+    def _fwd_bwd(self):
+        self.bucket.zero()
+        loss = self._forward()
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def _eager_step(self):
+        self._fwd_bwd()
+        self.bucket.all_reduce_mean()
+        self.opt.step()
+
+    def capture(self, warmup=3):
+        """Capture fwd+bwd and the optimizer step as two graphs around the (uncaptured) NCCL all-reduce."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        from .. import _lib
+        c0 = _lib.launch_count
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._fwd_bwd()
+        self.launches_per_step = _lib.launch_count - c0   # pasnl kernels captured in (and replayed by) one step
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt):
+            self.opt.step()
+        self.graph = True
+
+    def set_inputs(self, points, labels, smpw=None, non_blocking=True):
+        """Copy one batch (host pinned or device) into the static buffers."""
+        self.points.copy_(points, non_blocking=non_blocking)
+        self.labels.copy_(labels, non_blocking=non_blocking)
+        if smpw is not None and self.smpw is not None:
+            self.smpw.copy_(smpw, non_blocking=non_blocking)
+
+    def step(self):
+        if self.graph:
+            self.g_fb.replay()
+            self.bucket.all_reduce_mean()
+            self.g_opt.replay()
+        else:
+            self._eager_step()
+        return self.loss

@@ -1,0 +1,73 @@
+"""Data parallelism for the callers: one process per GPU, batches sharded by rank, ONE all-reduce per step.
+
+The reference is single-GPU only (no collective call sites), so this is new functionality; its
+contract is "N-rank gradients == the mean of the per-rank gradients" (per-replica batch-norm statistics, i.e. plain
+data-parallel replicas).  Every hot-path kernel is per-cloud, so there is no collective inside the path: the only
+exchange is the gradient bucket at the optimizer boundary -- all parameter gradients live in ONE flat fp32 buffer
+(``p.grad`` are views into it), reduced with a single NCCL all-reduce over NVLink/NVSwitch (gloo in CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBucket:
+    """Owns one contiguous fp32 buffer holding every parameter's gradient; ``p.grad`` alias slices of it."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradBucket needs at least one trainable parameter")
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("all parameters must be float32 on one device")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def check_aliasing(self):
+        """autograd must have accumulated in place (it does when .grad is pre-populated); guard against a silent
+        re-allocation that would detach a gradient from the bucket."""
+        base = self.flat.data_ptr()
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                raise RuntimeError("a parameter gradient no longer aliases the flat bucket")
+            off += p.numel()
+
+    def all_reduce_mean(self, group=None, async_op=False):
+        """Single collective: sum over ranks, then divide by the world size."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        world = dist.get_world_size(group)
+        if world == 1:
+            return None
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if async_op:
+            return work, world
+        self.flat.div_(world)
+        return None
+
+    def nbytes(self):
+        return self.numel * 4
+
+
+def shard_range(total, rank, world):
+    """Rank r's slice [lo, hi) of `total` independent clouds (strong scaling); remainders go to the low ranks."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value, device):
+    """MAX-reduce a python float over ranks (timings are reported as the slowest rank's)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
