@@ -216,7 +216,7 @@ def run_cpu_reference(args, batch, points, steps, warmup, threads=None):
     from oracle import cref, model_ref, refnative
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cref.set_threads(cores)
+    cref.set_threads(min(cores, batch))      # the C restatement parallelises over clouds, like the reference's kNN
     pc, labels, smpw = make_batch(args.workload, batch, points, 1)
     x = torch.from_numpy(pc)
     y = torch.from_numpy(labels)
@@ -238,7 +238,7 @@ def run_cpu_reference(args, batch, points, steps, warmup, threads=None):
         total = fwd()
         total.backward()
         opt.step()
-        return float(total)
+        return float(total.detach())
 
     for _ in range(warmup):
         one_step()

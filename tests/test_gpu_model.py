@@ -33,8 +33,27 @@ def no_dropout():
 
 
 def rel_l2(a, b):
-    a, b = a.double().flatten(), b.double().flatten()
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
     return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+def check_param_grads(grads, ref):
+    """Every parameter gradient within 2 % of its tensor norm.  Some gradients are identically zero in exact
+    arithmetic (e.g. the BN beta of the attention KEY projection: softmax is invariant to a per-query constant added
+    to all logits), where only rounding noise remains; those are held to an absolute floor of 1e-5 of the largest
+    gradient norm in the model instead of a meaningless relative bar."""
+    assert set(grads) == set(ref)
+    scale = max(float(ref[n].double().norm()) for n in ref)
+    rows = []
+    for n in grads:
+        err = float((grads[n].double() - ref[n].double()).norm())
+        bar = 2e-2 * float(ref[n].double().norm()) + 1e-5 * scale
+        rows.append((err / bar, n, err, float(ref[n].double().norm())))
+    rows.sort(reverse=True)
+    print("largest gradient errors relative to their bar (err/bar, name, |err|, |ref|):")
+    for r in rows[:5]:
+        print("   %.3f  %-45s %.3e %.3e" % r)
+    assert rows[0][0] < 1.0, rows[0]
 
 
 def test_sa_layer_with_adaptive_sampling_matches_oracle(cuda):
@@ -66,10 +85,7 @@ def test_sa_layer_with_adaptive_sampling_matches_oracle(cuda):
     torch.testing.assert_close(new_xyz.detach().cpu().double(), ox, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(new_pts.detach().cpu().double(), op, rtol=2e-3, atol=2e-3)
     assert rel_l2(feat.grad.cpu(), of) < 2e-2
-    assert set(grads) == set(og)
-    worst = max((rel_l2(grads[n], og[n]), n) for n in grads)
-    print("worst parameter-gradient rel-l2:", worst)
-    assert worst[0] < 2e-2, worst
+    check_param_grads(grads, og)
 
 
 @pytest.mark.parametrize("adaptive_sample", [False])
@@ -99,10 +115,7 @@ def test_cls_model_forward_backward_matches_oracle(cuda, adaptive_sample):
     print("oracle fp32-vs-fp64 logits gap %.2e; cuda-vs-fp64 %.2e" % (rel_l2(out[torch.float32][0], net64), rel_l2(pred.cpu(), net64)))
     torch.testing.assert_close(pred.detach().cpu().double(), net64, rtol=2e-3, atol=2e-3)
     assert abs(float(loss) - float(loss64)) <= 1e-4 * abs(float(loss64)) + 1e-5
-    assert set(grads) == set(g64)
-    worst = max((rel_l2(grads[n], g64[n]), n) for n in grads)
-    print("worst parameter-gradient rel-l2:", worst)
-    assert worst[0] < 2e-2, worst
+    check_param_grads(grads, g64)
 
 
 def test_seg_res_model_forward_backward_runs_and_matches_first_stage(cuda):
