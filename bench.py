@@ -161,6 +161,12 @@ def algorithmic_work(name, a):
     if name == "pasnl_nl_core_bwd":
         b, s, n, d = a[0:4]
         return 4 * b * (4 * s * d + 4 * n * d) + 8 * b * s, 10 * b * s * n * d, "tensor"
+    if name == "pasnl_bn_act_fwd":       # stats read + apply read/write of the (rows, c) activation
+        rows, c = a[0:2]
+        return 12 * rows * c, 8 * rows * c, "hbm"
+    if name == "pasnl_bn_act_bwd":       # reduce reads y, dout; apply reads y, dout, writes dy
+        rows, c = a[0:2]
+        return 20 * rows * c, 16 * rows * c, "hbm"
     return 0, 0, "hbm"
 
 

@@ -148,6 +148,24 @@ size_t pasnl_nl_core_bwd_workspace_bytes(int b, int s, int n, int d);
 int pasnl_nl_core_bwd(int b, int s, int n, int d, const float *q, const float *kv, const float *out, const float *lse,
                       float scale, const float *grad_out, float *grad_q, float *grad_kv, void *workspace, void *stream);
 
+/* ---------------------------------------------------------------- dense-glue epilogue (utils/tf_util.py:120-185,512-531) */
+
+/* Train-mode batch norm + activation over the output y (rows, c) of a 1x1 conv / fully-connected GEMM, replacing
+ * tf.nn.bias_add -> tf.contrib.layers.batch_norm(eps 1e-3, biased batch variance) -> activation_fn.
+ * The conv bias cancels inside batch norm, so it is NOT added to y: `bias` (c) or NULL is only used to keep
+ * moving_mean equal to what TF would store (mean(y) + bias).  act: 0 none, 1 relu, 2 leaky_relu(0.2).
+ * Outputs: out (rows, c); mean (c) = mean(y); var (c) = biased variance (both kept for the backward);
+ * running_mean / running_var (c) or NULL are updated in place: r = decay*r + (1-decay)*batch.
+ * workspace: pasnl_bn_workspace_bytes(c) bytes. */
+size_t pasnl_bn_workspace_bytes(int c);
+int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *gamma, const float *beta, float eps, int act,
+                     float *out, float *mean, float *var, const float *bias, float *running_mean, float *running_var,
+                     float decay, void *workspace, void *stream);
+/* Backward of the above: dout (rows, c) -> dy (rows, c) (the gradient w.r.t. the GEMM output), dgamma (c), dbeta (c). */
+int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *dout, const float *gamma, const float *beta,
+                     const float *mean, const float *var, float eps, int act, float *dy, float *dgamma, float *dbeta,
+                     void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,3 +359,51 @@ class NLCore(torch.autograd.Function):
         _call("pasnl_nl_core_bwd", b, s, n, d, _ptr(q), _ptr(kv), _ptr(out), _ptr(lse), ctx.scale, _ptr(grad_out),
               _ptr(gq), _ptr(gkv), _ptr(ws), _stream())
         return gq, gkv, None
+
+
+# ------------------------------------------------------------------ dense glue: GEMM + fused BN/activation epilogue
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+class DenseBNAct(torch.autograd.Function):
+    """act(batch_norm_train(x @ w + bias)) for a 1x1 conv / fully connected layer (tf_util.py:120-185,512-531).
+    The GEMMs are cuBLAS (torch.mm: plain library GEMMs); everything between them is two fused pasnl kernels forward
+    (statistics, normalise+activate) and two backward (reductions, apply).  The bias cancels inside train-mode batch
+    norm: it is not added and its gradient is exactly zero."""
+
+    @staticmethod
+    def forward(ctx, x, w2d, bias, gamma, beta, running_mean, running_var, decay, eps, act):
+        cin, cout = w2d.shape
+        x2 = x.reshape(-1, cin)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = torch.mm(x2, w2d)
+        rows = y.shape[0]
+        out = torch.empty_like(y)
+        mean = torch.empty((cout,), device=y.device, dtype=torch.float32)
+        var = torch.empty_like(mean)
+        ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
+        _call("pasnl_bn_act_fwd", rows, cout, _ptr(y), _ptr(gamma), _ptr(beta), float(eps), int(act), _ptr(out),
+              _ptr(mean), _ptr(var), _ptr(bias), _ptr(running_mean), _ptr(running_var), float(decay), _ptr(ws), _stream())
+        ctx.save_for_backward(x2, w2d, y, gamma, beta, mean, var)
+        ctx.meta = (float(eps), int(act), x.shape)
+        return out.reshape(x.shape[:-1] + (cout,))
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w2d, y, gamma, beta, mean, var = ctx.saved_tensors
+        eps, act, xshape = ctx.meta
+        rows, cout = y.shape
+        dout = dout.reshape(rows, cout)
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dy = torch.empty_like(y)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(beta)
+        ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
+        _call("pasnl_bn_act_bwd", rows, cout, _ptr(y), _ptr(dout), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), eps,
+              act, _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
+        dx = torch.mm(dy, w2d.t()).reshape(xshape) if ctx.needs_input_grad[0] else None
+        dw = torch.mm(x2.t(), dy) if ctx.needs_input_grad[1] else None
+        dbias = torch.zeros_like(gamma) if ctx.needs_input_grad[2] else None
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None

@@ -100,65 +100,91 @@ int scatter_rows_add(long rows, int rows_per_batch, int n, int c, long src_rows,
 
 // ---------------------------------------------------------------- fused SA-layer neighbourhood gather
 // out[row, :] = [ xyz[i] - center[q] | xyz[i] | feat[i] ]   (leading part only if center != nullptr)
-// One thread per output float: consecutive threads write consecutive floats (coalesced stores); the feature
-// part of a row is a contiguous read of the source row.
-__global__ void __launch_bounds__(kThreads) group_concat_kernel(long rows, int m, int nsample, int n, int c,
+// One WARP per output row: the row is decoded once (32-bit arithmetic), lanes then stride over its columns, so
+// both the feature read (one contiguous source row) and the output write (one contiguous output row) are coalesced.
+// (r01 used one thread per output float with 64-bit div/mod each: 130 instructions per float, 13 % of HBM peak.)
+// LPR = lanes per row (a power of two <= 32): narrow rows (cls layer 1: 9 floats) share a warp, wide rows get all 32 lanes.
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) group_concat_kernel(int rows, int m, int nsample, int n, int c,
                                                                 int idx_stride, const float *__restrict__ xyz,
                                                                 const float *__restrict__ feat,
                                                                 const int *__restrict__ idx,
                                                                 const float *__restrict__ center,
                                                                 float *__restrict__ out) {
+    constexpr int RPW = 32 / LPR;   // rows per warp per trip
     const int lead = center ? 3 : 0;
     const int w = lead + 3 + c;
-    const long total = rows * w;
-    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
-        const long row = g / w;  // (b, j, t) flattened
-        const int col = (int)(g - row * w);
-        const long q = row / nsample;  // (b, j) flattened
-        const int t = (int)(row - q * nsample);
-        const long bi = q / m;
-        const long srow = bi * n + __ldg(idx + q * idx_stride + t);
-        float v;
-        if (col < lead) {
-            v = __fsub_rn(__ldg(xyz + srow * 3 + col), __ldg(center + q * 3 + col));
-        } else if (col < lead + 3) {
-            v = __ldg(xyz + srow * 3 + (col - lead));
-        } else {
-            v = __ldg(feat + srow * c + (col - lead - 3));
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+    for (int row = warp * RPW + grp; row < rows; row += nwarps * RPW) {
+        const int q = row / nsample, t = row - q * nsample;
+        const int bi = q / m;
+        const size_t srow = (size_t)bi * n + __ldg(idx + (size_t)q * idx_stride + t);
+        float *o = out + (size_t)row * w;
+        const float *f = feat + srow * c;
+        for (int col = sub; col < w; col += LPR) {
+            float v;
+            if (col < lead) v = __fsub_rn(__ldg(xyz + srow * 3 + col), __ldg(center + (size_t)q * 3 + col));
+            else if (col < lead + 3) v = __ldg(xyz + srow * 3 + (col - lead));
+            else v = __ldg(f + (col - lead - 3));
+            o[col] = v;
         }
-        out[g] = v;
     }
 }
 
-// Backward: one thread per grad_out float.  Relative and absolute xyz parts both land in grad_xyz[i];
-// grad_center[q] accumulates minus the relative part.
-__global__ void __launch_bounds__(kThreads) group_concat_grad_kernel(long rows, int m, int nsample, int n, int c,
+// Backward: LPR lanes per grad_out row.  Relative and absolute xyz parts both land in grad_xyz[i];
+// grad_center[q] accumulates minus the relative part; the feature part is a coalesced row of reductions.
+template <int LPR, bool VEC4>
+__global__ void __launch_bounds__(kThreads) group_concat_grad_kernel(int rows, int m, int nsample, int n, int c,
                                                                      int idx_stride, int has_center,
                                                                      const float *__restrict__ grad_out,
                                                                      const int *__restrict__ idx,
                                                                      float *__restrict__ grad_xyz,
                                                                      float *__restrict__ grad_feat,
                                                                      float *__restrict__ grad_center) {
+    constexpr int RPW = 32 / LPR;
     const int lead = has_center ? 3 : 0;
     const int w = lead + 3 + c;
-    const long total = rows * w;
-    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < total; g += (long)gridDim.x * kThreads) {
-        const long row = g / w;
-        const int col = (int)(g - row * w);
-        const long q = row / nsample;
-        const int t = (int)(row - q * nsample);
-        const long bi = q / m;
-        const long srow = bi * n + __ldg(idx + q * idx_stride + t);
-        const float v = __ldg(grad_out + g);
-        if (col < lead) {
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+    for (int row = warp * RPW + grp; row < rows; row += nwarps * RPW) {
+        const int q = row / nsample, t = row - q * nsample;
+        const int bi = q / m;
+        const size_t srow = (size_t)bi * n + __ldg(idx + (size_t)q * idx_stride + t);
+        const float *g = grad_out + (size_t)row * w;
+        for (int col = sub; col < 3; col += LPR) {
+            float v = __ldg(g + lead + col);
+            if (lead) {
+                const float r = __ldg(g + col);
+                atomicAdd(grad_center + (size_t)q * 3 + col, -r);
+                v += r;
+            }
             atomicAdd(grad_xyz + srow * 3 + col, v);
-            atomicAdd(grad_center + q * 3 + col, -v);
-        } else if (col < lead + 3) {
-            atomicAdd(grad_xyz + srow * 3 + (col - lead), v);
+        }
+        const float *gf = g + lead + 3;
+        float *dst = grad_feat + srow * c;
+        if constexpr (VEC4) {
+            // destination rows are 16-byte aligned (c % 4 == 0); the source row is only 4/8-byte aligned
+            for (int v4 = sub; v4 < c / 4; v4 += LPR) {
+                float4 v;
+                v.x = __ldg(gf + v4 * 4 + 0);
+                v.y = __ldg(gf + v4 * 4 + 1);
+                v.z = __ldg(gf + v4 * 4 + 2);
+                v.w = __ldg(gf + v4 * 4 + 3);
+                atomicAdd(reinterpret_cast<float4 *>(dst + v4 * 4), v);   // red.global.add.v4.f32
+            }
         } else {
-            atomicAdd(grad_feat + srow * c + (col - lead - 3), v);
+            for (int col = sub; col < c; col += LPR) atomicAdd(dst + col, __ldg(gf + col));
         }
     }
+}
+
+int warp_grid(long rows, int rows_per_warp) {
+    long warps = (rows + rows_per_warp - 1) / rows_per_warp;
+    long blocks = (warps + (kThreads / 32) - 1) / (kThreads / 32);
+    const long cap = 148L * 16;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
 }
 
 // ---------------------------------------------------------------- three_interpolate
@@ -280,9 +306,16 @@ extern "C" int pasnl_group_concat(int b, int n, int c, int m, int nsample, const
     const long rows = (long)b * m * nsample;
     if (rows == 0) return PASNL_OK;
     PASNL_CHECK_ARG(xyz && idx && out && n >= 1 && (c == 0 || feat));
+    PASNL_CHECK_ARG(rows < (1L << 31));
     const int w = (center ? 3 : 0) + 3 + c;
-    group_concat_kernel<<<grid_for(rows * w), kThreads, 0, (cudaStream_t)stream>>>(rows, m, nsample, n, c, idx_stride,
-                                                                                   xyz, feat, idx, center, out);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GC_LAUNCH(LPR_) group_concat_kernel<LPR_><<<warp_grid(rows, 32 / LPR_), kThreads, 0, st>>>( \
+        (int)rows, m, nsample, n, c, idx_stride, xyz, feat, idx, center, out)
+    if (w <= 8) GC_LAUNCH(4);
+    else if (w <= 16) GC_LAUNCH(8);
+    else if (w <= 48) GC_LAUNCH(16);
+    else GC_LAUNCH(32);
+#undef GC_LAUNCH
     return pasnl_launch_status();
 }
 
@@ -310,9 +343,20 @@ extern "C" int pasnl_group_concat_grad(int b, int n, int c, int m, int nsample, 
     const long rows = (long)b * m * nsample;
     if (rows == 0) return PASNL_OK;
     PASNL_CHECK_ARG(grad_out && idx && n >= 1);
+    PASNL_CHECK_ARG(rows < (1L << 31));
     const int w = (has_center ? 3 : 0) + 3 + c;
-    group_concat_grad_kernel<<<grid_for(rows * w), kThreads, 0, st>>>(rows, m, nsample, n, c, idx_stride, has_center,
-                                                                      grad_out, idx, grad_xyz, grad_feat, grad_center);
+#define GCG_LAUNCH(LPR_, V_) group_concat_grad_kernel<LPR_, V_><<<warp_grid(rows, 32 / LPR_), kThreads, 0, st>>>( \
+        (int)rows, m, nsample, n, c, idx_stride, has_center, grad_out, idx, grad_xyz, grad_feat, grad_center)
+    if (c > 0 && c % 4 == 0 && aligned16(grad_feat)) {
+        if (w <= 48) GCG_LAUNCH(8, true);
+        else GCG_LAUNCH(32, true);
+    } else {
+        if (w <= 8) GCG_LAUNCH(4, false);
+        else if (w <= 16) GCG_LAUNCH(8, false);
+        else if (w <= 48) GCG_LAUNCH(16, false);
+        else GCG_LAUNCH(32, false);
+    }
+#undef GCG_LAUNCH
     return pasnl_launch_status();
 }
 

@@ -9,8 +9,13 @@ afterwards (AUTO_REUSE).  Dense math itself is plain PyTorch (cuBLAS): it is NOT
 re-implements -- only the call semantics matter: bias -> batch norm -> activation order
 (reference tf_util.py:170-185), NHWC layout, xavier init, BN eps 1e-3 with biased batch variance (:512-531).
 
-Documented deviations: moving_variance is updated with torch's unbiased batch variance (TF's non-fused
-contrib batch_norm uses the biased one); this affects inference-mode statistics only, never a training step.
+On CUDA tensors in training mode the sequence matmul -> bias -> batch norm -> activation runs as two cuBLAS GEMMs
+around the fused pasnl epilogue kernels (csrc/dense_glue.cu, `_ops.DenseBNAct`): two passes over the activation
+forward and two backward instead of ~8 / ~9.  The op-by-op path below remains for CPU tensors (unit tests of this
+mirror) and inference mode, and is checked against the fused path on the GPU (tests/test_gpu_glue.py).
+
+Documented deviations: on the op-by-op path moving_variance is updated with torch's unbiased batch variance (TF's
+non-fused contrib batch_norm, and the fused path here, use the biased one); inference-mode statistics only.
 """
 import contextlib
 import math
@@ -143,6 +148,35 @@ def _weights(shape, fan_in, fan_out, use_xavier, stddev, wd):
     return get_default_store().get_variable("weights", shape, init, wd=wd)
 
 
+# ---------------------------------------------------------------- fused GEMM + batch norm + activation (CUDA, training)
+def _act_code(activation_fn):
+    if activation_fn is None:
+        return 0
+    if activation_fn is relu:
+        return 1
+    if activation_fn is leaky_relu:
+        return 2
+    return None
+
+
+def _fused_dense_bn(x, w2d, bias, scope, bn_decay, is_training, activation_fn):
+    """conv/fc + bias + batch_norm(train) + activation through the fused pasnl epilogue; None if not applicable
+    (CPU tensors, inference mode, exotic activation): the caller then takes the op-by-op path."""
+    code = _act_code(activation_fn)
+    if not (x.is_cuda and bool(is_training) and code is not None and x.dtype == torch.float32):
+        return None
+    from . import _ops
+    store = get_default_store()
+    c = w2d.shape[1]
+    decay = 0.9 if bn_decay is None else float(bn_decay)
+    with store.variable_scope(scope):
+        beta = store.get_variable("beta", (c,), constant_init(0.0))
+        gamma = store.get_variable("gamma", (c,), constant_init(1.0))
+        mean = store.get_variable("moving_mean", (c,), constant_init(0.0), trainable=False)
+        var = store.get_variable("moving_variance", (c,), constant_init(1.0), trainable=False)
+    return _ops.DenseBNAct.apply(x, w2d, bias, gamma, beta, mean, var, decay, 1e-3, code)
+
+
 # ---------------------------------------------------------------- batch norm
 def batch_norm_template(inputs, is_training, scope, moments_dims_unused, bn_decay, data_format="NHWC"):
     """tf.contrib.layers.batch_norm(center=True, scale=True, decay=bn_decay, updates_collections=None), eps 1e-3
@@ -186,6 +220,10 @@ def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="S
     with store.variable_scope(scope):
         w = _weights((1, cin, num_output_channels), cin, num_output_channels, use_xavier, stddev, weight_decay)
         b = store.get_variable("biases", (num_output_channels,), constant_init(0.0))
+        if bn:
+            fused = _fused_dense_bn(inputs, w[0], b, "bn", bn_decay, is_training, activation_fn)
+            if fused is not None:
+                return fused
         out = torch.matmul(inputs, w[0]) + b
         if bn:
             out = batch_norm_for_conv1d(out, is_training, bn_decay, "bn", data_format)
@@ -210,11 +248,16 @@ def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], paddi
                      stddev, weight_decay)
         bias = store.get_variable("biases", (num_output_channels,), constant_init(0.0))
         if kw == 1:
-            out = torch.matmul(inputs, w[0, 0]) + bias
+            x_, w_ = inputs, w[0, 0]
         elif kw == wdt and padding == "VALID":
-            out = torch.matmul(inputs.reshape(b_, h, 1, wdt * cin), w.reshape(kw * cin, num_output_channels)) + bias
+            x_, w_ = inputs.reshape(b_, h, 1, wdt * cin), w.reshape(kw * cin, num_output_channels)
         else:
             raise NotImplementedError(f"conv2d mirror: kernel [1,{kw}] on width {wdt} with padding {padding}")
+        if bn:
+            fused = _fused_dense_bn(x_, w_, bias, "bn", bn_decay, is_training, activation_fn)
+            if fused is not None:
+                return fused
+        out = torch.matmul(x_, w_) + bias
         if bn:
             out = batch_norm_for_conv2d(out, is_training, bn_decay, "bn", data_format)
         if activation_fn is not None:
@@ -230,6 +273,10 @@ def fully_connected(inputs, num_outputs, scope, use_xavier=True, stddev=1e-3, we
     with store.variable_scope(scope):
         w = _weights((cin, num_outputs), cin, num_outputs, use_xavier, stddev, weight_decay)
         b = store.get_variable("biases", (num_outputs,), constant_init(0.0))
+        if bn:
+            fused = _fused_dense_bn(inputs, w, b, "bn", bn_decay, is_training, activation_fn)
+            if fused is not None:
+                return fused
         out = torch.matmul(inputs, w) + b
         if bn:
             out = batch_norm_for_fc(out, is_training, bn_decay, "bn")

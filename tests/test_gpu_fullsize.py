@@ -1,0 +1,120 @@
+"""BASELINE.json's full sizes (configs 4 and 5: ScanNet N=10240, SemanticKITTI N=65536) on the B200: exact
+comparisons where the oracle finishes in seconds (FPS, three_nn, kNN / attention on a query subset -- rows are
+independent) plus size-independent properties (self-first, sortedness, permutation, adjointness, linearity)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref, torch_ref
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def test_scannet_shape_fps_knn_interp(cuda):
+    from pointasnl_b200 import pointasnl_util, tf_interpolate, tf_sampling
+    pts, _, _ = synth.scannet_batch(4, 10240, 2, dup_frac=0.05)     # with the duplicated points data_rep creates
+    xyz = pts[:, :, :3].copy()
+    d = dev(xyz, cuda)
+    idx = tf_sampling.farthest_point_sample(1280, d)
+    assert np.array_equal(idx.cpu().numpy(), cref.fps(xyz, 1280))
+    sub = cref.gather_point(xyz, idx.cpu().numpy())
+    nn = pointasnl_util.knn_query(32, d, d)                          # layer0: self query, N = S = 10240
+    rng = np.random.default_rng(0)
+    pick = rng.choice(10240, 512, replace=False)
+    want = cref.knn(32, xyz, xyz[:, pick])
+    got = nn[:, pick].cpu().numpy()
+    # duplicates create exact ties: distances must agree position by position, indices wherever unambiguous
+    dg = ((xyz[np.arange(4)[:, None, None], got] - xyz[:, pick][:, :, None]) ** 2)
+    dw = ((xyz[np.arange(4)[:, None, None], want] - xyz[:, pick][:, :, None]) ** 2)
+    assert np.array_equal((dg[..., 0] + dg[..., 1]) + dg[..., 2], (dw[..., 0] + dw[..., 1]) + dw[..., 2])
+    assert np.array_equal(got, want)                                 # and our tie rule (ascending index) is the oracle's
+    dist, i3 = tf_interpolate.three_nn(d, dev(sub, cuda))            # fa_layer4: n=10240, m=1280
+    wd, wi = cref.three_nn(xyz, sub)
+    assert np.array_equal(i3.cpu().numpy(), wi) and np.array_equal(dist.cpu().numpy(), wd)
+
+
+def test_kitti_shape_fps_knn_threenn(cuda):
+    from pointasnl_b200 import pointasnl_util, tf_interpolate, tf_sampling
+    pts, _ = synth.kitti_batch(2, 65536, 3)
+    xyz = pts[:, :, :3].copy()
+    d = dev(xyz, cuda)
+    idx = tf_sampling.farthest_point_sample(8192, d)                 # cluster of 8 CTAs per cloud, 8191 rounds
+    cref.set_threads(2)
+    want = cref.fps(xyz, 8192)
+    cref.set_threads(1)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert all(len(set(r.tolist())) == 8192 for r in idx.cpu().numpy())
+    nn = pointasnl_util.knn_query(32, d, d)                          # N = S = 65536, K = 32: 8.6 G distances
+    nn_np = nn.cpu().numpy()
+    assert (nn_np[:, :, 0] == np.arange(65536)).all()                # the query itself first
+    pick = np.random.default_rng(1).choice(65536, 256, replace=False)
+    assert np.array_equal(nn_np[:, pick], cref.knn(32, xyz, xyz[:, pick]))
+    sub = cref.gather_point(xyz, want)
+    dist, i3 = tf_interpolate.three_nn(d, dev(sub, cuda))            # fa_layer4 of KITTI: n=65536, m=8192
+    cref.set_threads(2)
+    wd, wi = cref.three_nn(xyz, sub)
+    cref.set_threads(1)
+    assert np.array_equal(i3.cpu().numpy(), wi) and np.array_equal(dist.cpu().numpy(), wd)
+
+
+def test_kitti_shape_nonlocal_core_rows_and_linearity(cuda):
+    """KITTI layer1_1: S=8192 queries x N=65536 keys, D=32 (the reference would materialise a 4.3 GB map)."""
+    from pointasnl_b200 import _ops
+    torch.manual_seed(0)
+    b, s, n, dd = 2, 8192, 65536, 32
+    q = torch.randn(b, s, dd, device=cuda)
+    kv = torch.randn(b, n, 2 * dd, device=cuda)
+    scale = dd ** -0.5
+    out = _ops.NLCore.apply(q, kv, scale)
+    pick = torch.randperm(s)[:64]
+    want = torch_ref.nl_core(q[:, pick].cpu().double(), kv.cpu().double(), scale)
+    torch.testing.assert_close(out[:, pick].cpu().double(), want, rtol=1e-4, atol=1e-5)
+    # linear in V: core(q, [K | aV1 + V2]) = a core(q,[K|V1]) + core(q,[K|V2])
+    v2 = torch.randn(b, n, dd, device=cuda)
+    kv2 = torch.cat([kv[..., :dd], v2], -1)
+    kv3 = torch.cat([kv[..., :dd], 0.5 * kv[..., dd:] + v2], -1)
+    lhs = _ops.NLCore.apply(q, kv3, scale)
+    rhs = 0.5 * out + _ops.NLCore.apply(q, kv2, scale)
+    torch.testing.assert_close(lhs, rhs, rtol=1e-4, atol=1e-5)
+    # rows are convex combinations of V rows
+    assert float(out.abs().max()) <= float(kv[..., dd:].abs().max()) + 1e-5
+
+
+def test_kitti_shape_group_concat_adjoint(cuda):
+    from pointasnl_b200 import _ops
+    torch.manual_seed(1)
+    b, n, k = 2, 65536, 32
+    xyz = torch.randn(b, n, 3, device=cuda, requires_grad=True)
+    feat = torch.randn(b, n, 1, device=cuda, requires_grad=True)      # remission channel
+    idx = torch.randint(0, n, (b, n, k), device=cuda, dtype=torch.int32)
+    out = _ops.GroupConcat.apply(xyz, feat, idx, xyz.detach())
+    assert tuple(out.shape) == (b, n, k, 7)
+    g = torch.randn_like(out)
+    out.backward(g)
+    # <G(x), g> == <x, G^T g> for the linear parts
+    lhs = (out.detach()[..., 3:6].double() * g[..., 3:6].double()).sum() + \
+          ((out.detach()[..., :3] + xyz.detach()[:, :, None]).double() * g[..., :3].double()).sum()
+    rhs = (xyz.detach().double() * xyz.grad.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-4 * abs(float(lhs)) + 1e-2
+    lhs_f = (out.detach()[..., 6:].double() * g[..., 6:].double()).sum()
+    rhs_f = (feat.detach().double() * feat.grad.double()).sum()
+    assert abs(float(lhs_f - rhs_f)) <= 1e-4 * abs(float(lhs_f)) + 1e-2
+
+
+def test_seg_res_full_config4_step_runs(cuda):
+    """pointasnl_sem_seg_res at BASELINE config 4 (B=4, N=10240, xyz+rgb): one full training step, finite."""
+    from pointasnl_b200.callers.train_step import TrainStep
+    pts, labels, smpw = synth.scannet_batch(4, 10240, 2)
+    ts = TrainStep("seg", 4, 10240, cuda, use_graph=False)
+    ts.set_inputs(torch.from_numpy(pts), torch.from_numpy(labels), torch.from_numpy(smpw))
+    l0 = float(ts.step())
+    l1 = float(ts.step())
+    assert np.isfinite(l0) and np.isfinite(l1)
+    assert all(torch.isfinite(p.grad).all() for p in ts.store.parameters())
+    n_params = sum(p.numel() for p in ts.store.parameters())
+    assert 19_000_000 < n_params < 21_000_000       # ~19.8 M for pointasnl_sem_seg_res

@@ -1,0 +1,65 @@
+"""Fused dense-glue epilogue (csrc/dense_glue.cu) against the op-by-op PyTorch formulation of the reference's
+conv -> bias_add -> batch_norm(train, eps 1e-3, biased variance) -> activation (utils/tf_util.py:120-185,512-531)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_layer(x, w, b, gamma, beta, act):
+    y = x.reshape(-1, w.shape[0]) @ w + b
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    z = (y - mean) / torch.sqrt(var + 1e-3) * gamma + beta
+    if act == 1:
+        z = torch.relu(z)
+    elif act == 2:
+        z = torch.nn.functional.leaky_relu(z, 0.2)
+    return z.reshape(x.shape[:-1] + (w.shape[1],)), mean, var
+
+
+@pytest.mark.parametrize("shape,cout,act", [((4, 128, 64, 134), 128, 1), ((8, 512, 32, 9), 64, 1), ((32, 1536), 512, 1),
+                                            ((3, 50, 7, 35), 66, 0), ((2, 777, 5), 3, 2), ((6, 40, 1, 2048), 128, 1)])
+def test_fused_dense_bn_act_forward_backward(cuda, shape, cout, act):
+    from pointasnl_b200 import _ops
+    torch.manual_seed(cout)
+    cin = shape[-1]
+    x = torch.randn(*shape) * 1.7 + 0.3
+    w = torch.randn(cin, cout) / cin ** 0.5
+    b = torch.randn(cout)
+    gamma, beta = torch.rand(cout) + 0.5, torch.randn(cout) * 0.2
+    rm, rv = torch.zeros(cout), torch.ones(cout)
+    xd, wd, bd, gd, bed = [t.double().requires_grad_(True) for t in (x, w, b, gamma, beta)]
+    want, mean, var = reference_layer(xd, wd, bd, gd, bed, act)
+    xc, wc, bc, gc, bec = [t.to(cuda).requires_grad_(True) for t in (x, w, b, gamma, beta)]
+    rmc, rvc = rm.to(cuda), rv.to(cuda)
+    got = _ops.DenseBNAct.apply(xc, wc, bc, gc, bec, rmc, rvc, 0.9, 1e-3, act)
+    torch.testing.assert_close(got.detach().cpu().double(), want.detach(), rtol=1e-4, atol=2e-5)
+    # moving statistics as TF keeps them: decay*old + (1-decay)*batch, mean includes the conv bias
+    torch.testing.assert_close(rmc.cpu().double(), 0.1 * mean.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rvc.cpu().double(), 0.9 + 0.1 * var.detach(), rtol=1e-4, atol=1e-5)
+    g = torch.randn(got.shape)
+    want.backward(g.double())
+    got.backward(g.to(cuda))
+    for name, a, r in (("x", xc, xd), ("w", wc, wd), ("gamma", gc, gd), ("beta", bec, bed)):
+        err = (a.grad.cpu().double() - r.grad).norm() / r.grad.norm().clamp(min=1e-12)
+        assert err < 1e-4, (name, float(err))
+    assert float(bc.grad.abs().max()) == 0.0          # exact: the bias cancels inside train-mode batch norm
+    assert float(bd.grad.abs().max()) < 1e-9 * float(wd.grad.abs().max()) + 1e-12
+
+
+def test_tf_util_layers_take_the_fused_path_and_match_op_by_op(cuda):
+    from pointasnl_b200 import _lib, tf_util
+    torch.manual_seed(0)
+    x = torch.randn(4, 64, 16, 20, device=cuda)
+    store = tf_util.VariableStore(cuda, seed=5)
+    with store.as_default():
+        c0 = _lib.launch_count
+        fused = tf_util.conv2d(x, 24, [1, 1], "c", padding="VALID", bn=True, is_training=True)
+        assert _lib.launch_count - c0 == 4            # memset + stats + finalize + apply
+        orig = tf_util._fused_dense_bn
+        tf_util._fused_dense_bn = lambda *a, **k: None
+        try:
+            plain = tf_util.conv2d(x, 24, [1, 1], "c", padding="VALID", bn=True, is_training=True)
+        finally:
+            tf_util._fused_dense_bn = orig
+    torch.testing.assert_close(fused, plain, rtol=1e-4, atol=1e-5)
