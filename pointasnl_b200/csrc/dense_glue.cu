@@ -128,29 +128,53 @@ __global__ void bn_finalize_kernel(long rows, int c, const float *__restrict__ y
     if (running_var) running_var[ch] = decay * running_var[ch] + (1.f - decay) * (float)v;
 }
 
-// out = act((y - mean) * rstd * gamma + beta)
+// out = act((y - mean) * rstd * gamma + beta).  Same (row-lane, channel-group) thread layout as the statistics
+// pass: a thread keeps its channels' parameters in registers and streams rows, so the only memory instructions in
+// the loop are the data loads/stores themselves.
 template <int VEC>
-__global__ void bn_apply_kernel(long total_vec, int c, int cvec, const float *__restrict__ y,
+__global__ void bn_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                 const float *__restrict__ mean, const float *__restrict__ var,
                                 const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int act,
                                 float *__restrict__ out) {
-    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total_vec; g += (long)gridDim.x * blockDim.x) {
-        const int col = (int)(g % cvec) * VEC;
-        float x[VEC], o[VEC];
-        if constexpr (VEC == 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(y) + g);
-            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-        } else {
-            x[0] = __ldg(y + g);
+    const int t = threadIdx.x, cv = t % cvec, ry = t / cvec;
+    const int col = cv * VEC;
+    float mu[VEC], sc[VEC], be[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        mu[v] = __ldg(mean + col + v);
+        sc[v] = rsqrtf(__ldg(var + col + v) + eps) * __ldg(gamma + col + v);
+        be[v] = __ldg(beta + col + v);
+    }
+    const long chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+    constexpr int U = 4;
+    for (long rb = r0 + ry; rb < r1; rb += (long)rpb * U) {
+        float x[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long r = rb + (long)u * rpb;
+            if (r < r1) {
+                if constexpr (VEC == 4) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(y + r * c + col));
+                    x[u][0] = q.x; x[u][1] = q.y; x[u][2] = q.z; x[u][3] = q.w;
+                } else {
+                    x[u][0] = __ldg(y + r * c + col);
+                }
+            }
         }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const float rstd = rsqrtf(__ldg(var + col + v) + eps);
-            const float sc = rstd * __ldg(gamma + col + v);
-            o[v] = activate(fmaf(x[v] - __ldg(mean + col + v), sc, __ldg(beta + col + v)), act);
+        for (int u = 0; u < U; ++u) {
+            const long r = rb + (long)u * rpb;
+            if (r < r1) {
+                float o[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) o[v] = activate(fmaf(x[u][v] - mu[v], sc[v], be[v]), act);
+                if constexpr (VEC == 4)
+                    *reinterpret_cast<float4 *>(out + r * c + col) = make_float4(o[0], o[1], o[2], o[3]);
+                else
+                    out[r * c + col] = o[0];
+            }
         }
-        if constexpr (VEC == 4) reinterpret_cast<float4 *>(out)[g] = make_float4(o[0], o[1], o[2], o[3]);
-        else out[g] = o[0];
     }
 }
 
@@ -230,7 +254,7 @@ __global__ void bn_bwd_reduce_kernel(long rows, int c, int cvec, int rpb, const 
 
 // dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz*xhat)); block 0 also emits dgamma / dbeta
 template <int VEC>
-__global__ void bn_bwd_apply_kernel(long rows, long total_vec, int c, int cvec, const float *__restrict__ y,
+__global__ void bn_bwd_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                     const float *__restrict__ dout, const float *__restrict__ mean,
                                     const float *__restrict__ var, const float *__restrict__ gamma,
                                     const float *__restrict__ beta, float eps, int act,
@@ -241,31 +265,57 @@ __global__ void bn_bwd_apply_kernel(long rows, long total_vec, int c, int cvec, 
             dbeta[ch] = (float)ws[ch];
             dgamma[ch] = (float)ws[c + ch];
         }
+    const int t = threadIdx.x, cv = t % cvec, ry = t / cvec;
+    const int col = cv * VEC;
     const float inv_n = (float)(1.0 / (double)rows);
-    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total_vec; g += (long)gridDim.x * blockDim.x) {
-        const int col = (int)(g % cvec) * VEC;
-        float x[VEC], d[VEC], o[VEC];
-        if constexpr (VEC == 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(y) + g);
-            const float4 w = __ldg(reinterpret_cast<const float4 *>(dout) + g);
-            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-            d[0] = w.x; d[1] = w.y; d[2] = w.z; d[3] = w.w;
-        } else {
-            x[0] = __ldg(y + g);
-            d[0] = __ldg(dout + g);
+    float mu[VEC], rstd[VEC], sc[VEC], be[VEC], m1[VEC], m2[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        mu[v] = __ldg(mean + col + v);
+        rstd[v] = rsqrtf(__ldg(var + col + v) + eps);
+        sc[v] = rstd[v] * __ldg(gamma + col + v);
+        be[v] = __ldg(beta + col + v);
+        m1[v] = (float)ws[col + v] * inv_n;
+        m2[v] = (float)ws[c + col + v] * inv_n;
+    }
+    const long chunk = (rows + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+    constexpr int U = 2;
+    for (long rb = r0 + ry; rb < r1; rb += (long)rpb * U) {
+        float x[U][VEC], d[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long r = rb + (long)u * rpb;
+            if (r < r1) {
+                if constexpr (VEC == 4) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(y + r * c + col));
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(dout + r * c + col));
+                    x[u][0] = q.x; x[u][1] = q.y; x[u][2] = q.z; x[u][3] = q.w;
+                    d[u][0] = w.x; d[u][1] = w.y; d[u][2] = w.z; d[u][3] = w.w;
+                } else {
+                    x[u][0] = __ldg(y + r * c + col);
+                    d[u][0] = __ldg(dout + r * c + col);
+                }
+            }
         }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const float rstd = rsqrtf(__ldg(var + col + v) + eps);
-            const float ga = __ldg(gamma + col + v);
-            const float xc = x[v] - __ldg(mean + col + v);
-            const float z = fmaf(xc, rstd * ga, __ldg(beta + col + v));
-            const float dz = d[v] * act_grad(z, act);
-            const float m1 = (float)ws[col + v] * inv_n, m2 = (float)ws[c + col + v] * inv_n;
-            o[v] = ga * rstd * (dz - m1 - xc * rstd * m2);
+        for (int u = 0; u < U; ++u) {
+            const long r = rb + (long)u * rpb;
+            if (r < r1) {
+                float o[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float xc = x[u][v] - mu[v];
+                    const float z = fmaf(xc, sc[v], be[v]);
+                    const float dz = d[u][v] * act_grad(z, act);
+                    o[v] = sc[v] * (dz - m1[v] - xc * rstd[v] * m2[v]);
+                }
+                if constexpr (VEC == 4)
+                    *reinterpret_cast<float4 *>(dy + r * c + col) = make_float4(o[0], o[1], o[2], o[3]);
+                else
+                    dy[r * c + col] = o[0];
+            }
         }
-        if constexpr (VEC == 4) reinterpret_cast<float4 *>(dy)[g] = make_float4(o[0], o[1], o[2], o[3]);
-        else dy[g] = o[0];
     }
 }
 
@@ -274,6 +324,11 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 int stream_grid(long work, int threads) {
     long blocks = (work + threads - 1) / threads;
     if (blocks > 148L * 32) blocks = 148L * 32;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+int apply_grid(long rows, int rpb) {
+    long blocks = (rows + (long)rpb * 8 - 1) / ((long)rpb * 8);     // >= 8 rows per thread-row
+    if (blocks > 148L * 16) blocks = 148L * 16;
     return (int)(blocks < 1 ? 1 : blocks);
 }
 int reduce_grid(long rows, int rpb) {
@@ -299,19 +354,17 @@ extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *g
     PASNL_CHECK_ARG(s.threads <= 1024);
     const size_t smem = sizeof(float) * 2 * (size_t)s.threads * s.vec;
     const int rg = reduce_grid(rows, s.rpb);
-    const long total_vec = rows * s.cvec;
+    const int ag = apply_grid(rows, s.rpb);
     if (s.vec == 4) {
         bn_stats_kernel<4><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
         bn_finalize_kernel<<<ceil_div_i(c, 128), 128, 0, st>>>(rows, c, y, ws, mean, var, bias, running_mean,
                                                                running_var, decay);
-        bn_apply_kernel<4><<<stream_grid(total_vec, 256), 256, 0, st>>>(total_vec, c, s.cvec, y, mean, var, gamma, beta,
-                                                                       eps, act, out);
+        bn_apply_kernel<4><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, mean, var, gamma, beta, eps, act, out);
     } else {
         bn_stats_kernel<1><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
         bn_finalize_kernel<<<ceil_div_i(c, 128), 128, 0, st>>>(rows, c, y, ws, mean, var, bias, running_mean,
                                                                running_var, decay);
-        bn_apply_kernel<1><<<stream_grid(total_vec, 256), 256, 0, st>>>(total_vec, c, s.cvec, y, mean, var, gamma, beta,
-                                                                       eps, act, out);
+        bn_apply_kernel<1><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, mean, var, gamma, beta, eps, act, out);
     }
     return pasnl_launch_status();
 }
@@ -329,17 +382,17 @@ extern "C" int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *d
     PASNL_CHECK_ARG(s.threads <= 1024);
     const size_t smem = sizeof(float) * 2 * (size_t)s.threads * s.vec;
     const int rg = reduce_grid(rows, s.rpb);
-    const long total_vec = rows * s.cvec;
+    const int ag = apply_grid(rows, s.rpb);
     if (s.vec == 4) {
         bn_bwd_reduce_kernel<4><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, dout, mean, var, gamma, beta, eps,
                                                             act, ws);
-        bn_bwd_apply_kernel<4><<<stream_grid(total_vec, 256), 256, 0, st>>>(rows, total_vec, c, s.cvec, y, dout, mean, var,
-                                                                           gamma, beta, eps, act, ws, dy, dgamma, dbeta);
+        bn_bwd_apply_kernel<4><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, dout, mean, var, gamma, beta, eps, act,
+                                                        ws, dy, dgamma, dbeta);
     } else {
         bn_bwd_reduce_kernel<1><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, dout, mean, var, gamma, beta, eps,
                                                             act, ws);
-        bn_bwd_apply_kernel<1><<<stream_grid(total_vec, 256), 256, 0, st>>>(rows, total_vec, c, s.cvec, y, dout, mean, var,
-                                                                           gamma, beta, eps, act, ws, dy, dgamma, dbeta);
+        bn_bwd_apply_kernel<1><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, dout, mean, var, gamma, beta, eps, act,
+                                                        ws, dy, dgamma, dbeta);
     }
     return pasnl_launch_status();
 }

@@ -38,6 +38,32 @@ struct __align__(16) Slot {  // one candidate: 32 bytes
 constexpr int kMaxWarps = 32;
 constexpr int kMaxCluster = 8;
 
+// ---- DSMEM exchange primitives (cluster path): remote shared-memory stores that complete a transaction count on
+// the RECEIVER's mbarrier, so a round needs no cluster-wide barrier -- each CTA just waits for its csize slots.
+__device__ __forceinline__ uint32_t map_to_rank(const void *local_smem, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t dst, unsigned a, unsigned b, unsigned c, unsigned d, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "XWAIT:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra XDONE;\n\t"
+        "bra XWAIT;\n\t"
+        "XDONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // Reduce (bits, tk) over the warp: returns true on the single winning lane.
 __device__ __forceinline__ bool warp_argmax(unsigned bits, unsigned tk, unsigned &wbits, unsigned &wtk) {
     wbits = __reduce_max_sync(FULL_MASK, bits);
@@ -53,6 +79,7 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(int n, int m, int chunk, c
     __shared__ Slot wslot[2][NW];            // per-warp winners, double buffered over rounds
     __shared__ Slot cslot[2][kMaxCluster];   // per-CTA winners of the cluster (written by peers through DSMEM)
     __shared__ uint64_t bar;
+    __shared__ uint64_t xbar[2];             // receive barriers of the DSMEM exchange, one per slot buffer
 
     int cloud, rank = 0, csize = 1;
     if constexpr (CLUSTER) {
@@ -75,9 +102,13 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(int n, int m, int chunk, c
     float *buf = reinterpret_cast<float *>(smem_raw);
     if (t == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    if constexpr (CLUSTER) cg::this_cluster().sync();   // peers' receive barriers exist before anybody sends
+    uint32_t xparity = 0;                               // bit pb = phase parity of xbar[pb]
     const float *pts = stage_floats(buf, cloud_xyz + (size_t)base * 3, cnt * 3, &bar);
     stage_wait(&bar, 0);
 
@@ -138,20 +169,17 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(int n, int m, int chunk, c
         src = max(src, 0);
 
         if constexpr (CLUSTER) {
-            cg::cluster_group cluster = cg::this_cluster();
-            // warp 0 publishes this CTA's winner into every CTA's cslot[pb][rank]
+            // warp 0 pushes this CTA's winner into cslot[pb][rank] of EVERY CTA of the cluster (itself included)
+            // with st.async; each receiver's mbarrier completes when all csize x 16 bytes x 2 have landed.
+            if (t == 0) mbar_expect_tx(&xbar[pb], (uint32_t)csize * 32u);
             if (warp == 0 && lane < csize) {
-                Slot *remote = cluster.map_shared_rank(&cslot[pb][rank], lane);
-                Slot s;
-                s.bits = cbits;
-                s.tk = ctk;
-                s.x = wslot[pb][src].x;
-                s.y = wslot[pb][src].y;
-                s.z = wslot[pb][src].z;
-                s.pad[0] = s.pad[1] = s.pad[2] = 0;
-                *remote = s;
+                const uint32_t dst = map_to_rank(&cslot[pb][rank], lane);
+                const uint32_t rbar = map_to_rank(&xbar[pb], lane);
+                st_async_v4(dst, cbits, ctk, __float_as_uint(wslot[pb][src].x), __float_as_uint(wslot[pb][src].y), rbar);
+                st_async_v4(dst + 16, __float_as_uint(wslot[pb][src].z), 0u, 0u, 0u, rbar);
             }
-            cluster.sync();
+            mbar_wait_cluster(&xbar[pb], (xparity >> pb) & 1u);
+            xparity ^= 1u << pb;
             unsigned gbits = 0u, gtk = 0xffffffffu;
             if (lane < csize) {
                 gbits = cslot[pb][lane].bits;
@@ -273,9 +301,14 @@ extern "C" int pasnl_fps(int b, int n, int m, const float *xyz, void *workspace,
         fps_generic_kernel<<<b, 1024, 0, st>>>(n, m, xyz, (float *)workspace, out_idx);
         return pasnl_launch_status();
     }
-    // cluster size: smallest power of two whose CTAs hold <= kMaxChunk points each
+    // Cluster size.  FPS is a latency chain of m rounds; a round costs (register sweep over the CTA's points) +
+    // (intra-CTA reduction) [+ DSMEM exchange].  Up to 2048 points one CTA is fastest; above that the sweep dominates,
+    // so the cloud is spread over a cluster (<= 8 CTAs, the portable maximum) of ~1280-point CTAs, growing the per-CTA
+    // slice only when 8 CTAs are not enough.
     int csize = 1;
-    while ((long)csize * kMaxChunk < n) csize *= 2;
+    if (n > 2048) {
+        while (csize < kMaxCluster && (long)csize * 1280 < n) csize *= 2;
+    }
     int chunk = (n + csize - 1) / csize;
     chunk = (chunk + 3) & ~3;  // keeps every slice 16-byte aligned relative to the cloud start
     // threads / points-per-thread for the per-CTA slice
@@ -284,6 +317,7 @@ extern "C" int pasnl_fps(int b, int n, int m, const float *xyz, void *workspace,
     if (chunk <= 256) FPS_CASE(2, 128);
     if (chunk <= 512) FPS_CASE(4, 128);
     if (chunk <= 1024) FPS_CASE(4, 256);
+    if (chunk <= 1280) FPS_CASE(5, 256);
     if (chunk <= 2048) FPS_CASE(4, 512);
     if (chunk <= 3072) FPS_CASE(6, 512);
     if (chunk <= 4096) FPS_CASE(4, 1024);

@@ -7,11 +7,32 @@ attention + re-sampling, the Non-Local attention) is one ``pasnl_*`` CUDA kernel
 BN / ReLU glue between them is PyTorch (cuBLAS), see tf_util.py.
 """
 import math
+import weakref
 
 import torch
 
 from . import _ops, tf_grouping, tf_interpolate, tf_sampling, tf_util
 from .tf_interpolate import three_interpolate, three_nn  # noqa: F401  (re-exported like the reference module)
+
+
+# ---------------------------------------------------------------------------------------------- memoisation
+# FPS and the neighbour searches are pure functions of coordinates.  pointasnl_sem_seg_res runs layer1_1 and
+# layer1_2 on the very same inputs (reference models/pointasnl_sem_seg_res.py:35-36: FPS 10240->1280 and kNN twice),
+# so results are memoised per source TENSOR OBJECT (weak reference + version counter: an in-place edit or a new
+# tensor at a recycled address can never alias a stale entry).
+_memo = {}
+
+
+def _memoized(tag, srcs, extra, fn):
+    key = (tag, tuple(id(t) for t in srcs), extra)
+    hit = _memo.get(key)
+    if hit is not None and all(r() is t and v == t._version for r, v, t in zip(hit[0], hit[1], srcs)):
+        return hit[2]
+    res = fn()
+    if len(_memo) >= 16:
+        _memo.clear()
+    _memo[key] = ([weakref.ref(t) for t in srcs], [t._version for t in srcs], res)
+    return res
 
 
 # ---------------------------------------------------------------------------------------------- point-set functions
@@ -25,18 +46,21 @@ def knn_query(k, support_pts, query_pts):
 def sampling(npoint, pts, feature=None):
     """pts (B, N, D) -> sub_pts (B, npoint, D) [, sub_feature (B, npoint, C)] by farthest point sampling on pts
     (reference :33-49).  Differentiable w.r.t. pts / feature (tf.gather_nd semantics)."""
-    fps_idx = tf_sampling.farthest_point_sample(npoint, pts.detach())
-    sub = _ops.GatherRows.apply(pts, fps_idx)
+    def run():
+        idx = tf_sampling.farthest_point_sample(npoint, pts.detach())
+        return idx, _ops.GatherRows.apply(pts, idx)
+    fps_idx, sub = _memoized("fps", (pts,), int(npoint), run)
     if feature is None:
         return sub
     return sub, _ops.GatherRows.apply(feature, fps_idx)
 
 
 def _neighbor_idx(K, src_xyz, q_xyz, use_knn, radius):
-    if use_knn:
-        return knn_query(K, src_xyz.detach(), q_xyz.detach())
-    idx, _ = tf_grouping.query_ball_point(radius, K, src_xyz.detach(), q_xyz.detach())
-    return idx
+    def run():
+        if use_knn:
+            return knn_query(K, src_xyz.detach(), q_xyz.detach())
+        return tf_grouping.query_ball_point(radius, K, src_xyz.detach(), q_xyz.detach())[0]
+    return _memoized("nbr", (src_xyz, q_xyz), (int(K), bool(use_knn), radius), run)
 
 
 def grouping(feature, K, src_xyz, q_xyz, use_xyz=True, use_knn=True, radius=0.2):
