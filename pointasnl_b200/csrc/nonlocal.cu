@@ -15,6 +15,8 @@
 // Thread layout: 256 threads = 16 (ty) x 16 (tx); thread (ty,tx) owns rows ty*4..+3 and, for the score tile,
 // columns tx*RN..+RN-1.  Operand tiles for the score products are stored TRANSPOSED in shared memory ([d][row]) so
 // that one LDS.128 fetches the 4 rows / 4 columns a thread needs for a given d.
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace pasnl;
@@ -399,12 +401,27 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 }  // namespace
 
+// tcgen05 / TMEM implementation (nonlocal_tc.cu)
+int pasnl_nl_core_fwd_tc(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
+                         float *lse, cudaStream_t st);
+
+static bool use_tensor_core_path(int s, int n, int d) {
+    // A 128-query x 64-key x d tile must be worth filling: tiny problems (deep seg layers: s=40, n=80) and widths the
+    // tcgen05 kernel is not instantiated for stay on the CUDA-core kernel.  PASNL_NL_FWD=simt|tc overrides (profiling).
+    static const char *force = getenv("PASNL_NL_FWD");
+    if (force && force[0] == 's') return false;
+    const bool shape_ok = (d == 32 || d == 64);
+    if (force && force[0] == 't') return shape_ok;
+    return shape_ok && s >= 64 && n >= 128;
+}
+
 extern "C" int pasnl_nl_core_fwd(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
                                  float *lse, void *stream) {
     PASNL_CHECK_ARG(b >= 0 && s >= 0 && n >= 1 && d >= 4 && d <= 128 && d % 4 == 0 && b <= 65535);
     if ((long)b * s == 0) return PASNL_OK;
     PASNL_CHECK_ARG(q && kv && out && lse && aligned16(q) && aligned16(kv));
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_tensor_core_path(s, n, d) && aligned16(out)) return pasnl_nl_core_fwd_tc(b, s, n, d, q, kv, scale, out, lse, st);
     if (d <= 32) return launch_fwd<32>(b, s, n, d, q, kv, scale, out, lse, st);
     if (d <= 64) return launch_fwd<64>(b, s, n, d, q, kv, scale, out, lse, st);
     return launch_fwd<128>(b, s, n, d, q, kv, scale, out, lse, st);
