@@ -166,6 +166,13 @@ int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *dout, const 
                      const float *mean, const float *var, float eps, int act, float *dy, float *dgamma, float *dbeta,
                      void *workspace, void *stream);
 
+/* fp32-accurate GEMM of the 1x1-conv / fully-connected layers on tcgen05 tensor cores (3xTF32 split, fp32 TMEM
+ * accumulation; replaces tf.nn.conv2d / tf.matmul of tf_util.py:120-185,318-355 and their input gradients):
+ *     C[rows, n] = A[rows, k] . Bt[n, k]^T ,   A, Bt, C row-major with leading dimensions lda, ldb, ldc (floats).
+ * forward: A = x, Bt = W^T;  input gradient: A = dy, Bt = W. */
+int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb, float *C,
+                           long ldc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -364,6 +364,25 @@ class NLCore(torch.autograd.Function):
 # ------------------------------------------------------------------ dense glue: GEMM + fused BN/activation epilogue
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
+GEMM_MIN_ROWS = 512   # below this a 128-row tile grid cannot fill the GPU: cuBLAS takes those (fc layers, rows = batch)
+
+
+def gemm_rows(a, bt):
+    """a (rows, k) @ bt (n, k)^T -> (rows, n), fp32-accurate, on tcgen05 (pasnl_gemm_rows_tf32x3) when the problem is
+    tall enough, cuBLAS otherwise.  Both operands row-major with a unit inner stride."""
+    rows, k = a.shape
+    n = bt.shape[0]
+    if rows < GEMM_MIN_ROWS or not a.is_cuda:
+        return torch.mm(a, bt.t())
+    if a.stride(1) != 1:
+        a = a.contiguous()
+    if bt.stride(1) != 1:
+        bt = bt.contiguous()
+    c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
+    _call("pasnl_gemm_rows_tf32x3", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(bt), int(bt.stride(0)), _ptr(c), n,
+          _stream())
+    return c
+
 
 class DenseBNAct(torch.autograd.Function):
     """act(batch_norm_train(x @ w + bias)) for a 1x1 conv / fully connected layer (tf_util.py:120-185,512-531).
@@ -377,7 +396,7 @@ class DenseBNAct(torch.autograd.Function):
         x2 = x.reshape(-1, cin)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        y = torch.mm(x2, w2d)
+        y = gemm_rows(x2, w2d.t().contiguous())          # x.W on tensor cores (3xTF32)
         rows = y.shape[0]
         out = torch.empty_like(y)
         mean = torch.empty((cout,), device=y.device, dtype=torch.float32)
@@ -403,7 +422,7 @@ class DenseBNAct(torch.autograd.Function):
         ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
         _call("pasnl_bn_act_bwd", rows, cout, _ptr(y), _ptr(dout), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), eps,
               act, _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
-        dx = torch.mm(dy, w2d.t()).reshape(xshape) if ctx.needs_input_grad[0] else None
+        dx = gemm_rows(dy, w2d).reshape(xshape) if ctx.needs_input_grad[0] else None   # dy.W^T: Bt = W as stored
         dw = torch.mm(x2.t(), dy) if ctx.needs_input_grad[1] else None
         dbias = torch.zeros_like(gamma) if ctx.needs_input_grad[2] else None
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None

@@ -1,0 +1,244 @@
+// gemm_tc.cu -- fp32-accurate "rows" GEMM on tcgen05 tensor cores (3xTF32 split, TMEM accumulators), sm_100a.
+//
+//     C[rows, n] = A[rows, k] . Bt[n, k]^T          (A and Bt row-major: the contraction index is contiguous in both)
+//
+// This is the shape of every 1x1-conv / fully-connected layer around the point-set ops:
+// forward y = x.W (Bt = W^T), input gradient dx = dy.W^T (Bt = W).  rows = B*S*K is 10^4..10^6, k and n are 3..4096.
+// cuBLAS runs these as fp32 SIMT SGEMMs (~50 TFLOP/s, 5.5 ms of a 11.5 ms cls step); a single TF32 pass would break the
+// 1e-4 parity bar, so each product is split a = a_hi + a_lo (tf32 round-to-nearest) and accumulated as
+// a_hi.b_hi + a_hi.b_lo + a_lo.b_hi in fp32 TMEM (error ~2^-21 relative).  At 3 MMAs per k-step the tensor pipe still
+// outruns HBM for these skinny shapes, so the kernel is memory bound: bytes = 4*rows*(k+n).
+//
+// CTA = 128 threads = one 128-row x NT-column output tile; k is consumed in 32-wide chunks:
+//   all threads load + split the A (128 x 32) and Bt (NT x 32) chunks into the canonical no-swizzle K-major UMMA
+//   layout [k/4][row][4] (hi and lo copies), one thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT),
+//   tcgen05.commit -> mbarrier; after the last chunk every thread tcgen05.ld's its row and the tile leaves through a
+//   shared-memory transpose so that global stores are coalesced.  Latency is hidden by co-resident CTAs (64-96 KB of
+//   shared memory, 32..256 TMEM columns each), not by an intra-CTA pipeline, in this revision.
+#include "common.cuh"
+
+using namespace pasnl;
+
+namespace gtc {
+
+constexpr int kM = 128;
+constexpr int kKC = 32;     // k chunk
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 4 consecutive k of one row, zero past the matrix edge; vector load when the row pitch allows it
+template <bool VEC4>
+__device__ __forceinline__ float4 load4(const float *__restrict__ base, long row, long rows, long ld, int k0, int k) {
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows) {
+        const float *p = base + row * ld + k0;
+        if constexpr (VEC4) {
+            if (k0 + 3 < k) return __ldg(reinterpret_cast<const float4 *>(p));
+        }
+        if (k0 < k) x.x = __ldg(p);
+        if (k0 + 1 < k) x.y = __ldg(p + 1);
+        if (k0 + 2 < k) x.z = __ldg(p + 2);
+        if (k0 + 3 < k) x.w = __ldg(p + 3);
+    }
+    return x;
+}
+__device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int row, int kc, float4 x) {
+    float4 h, l;
+    h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+    l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+    const int o = (kc * rows + row) * 4;
+    *reinterpret_cast<float4 *>(hi + o) = h;
+    *reinterpret_cast<float4 *>(lo + o) = l;
+}
+
+constexpr int tmem_cols(int nt) { return nt < 32 ? 32 : nt; }   // power of two >= 32 (NT is 32/64/128/256)
+
+template <int NT, bool VEC4>
+__global__ void __launch_bounds__(kM) gemm_rows_kernel(long rows, int k, int n, const float *__restrict__ A, long lda,
+                                                       const float *__restrict__ Bt, long ldb, float *__restrict__ C,
+                                                       long ldc) {
+    extern __shared__ __align__(128) float smem[];
+    float *Ahi = smem, *Alo = Ahi + kM * kKC;                     // [8][128][4]
+    float *Bhi = Alo + kM * kKC, *Blo = Bhi + NT * kKC;           // [8][NT][4]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const long row0 = (long)blockIdx.x * kM;
+    const int n0 = blockIdx.y * NT;
+    const int nvalid = min(NT, n - n0);
+
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(tmem_cols(NT))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    constexpr uint32_t idesc = make_idesc(kM, NT);
+
+    uint32_t phase = 0;
+    for (int kb = 0; kb < k; kb += kKC) {
+        // ---- load + split this k-chunk of A (128 rows) and Bt (NT rows)
+#pragma unroll
+        for (int kc = 0; kc < kKC / 4; ++kc)
+            store_split4(Ahi, Alo, kM, t, kc, load4<VEC4>(A, row0 + t, rows, lda, kb + kc * 4, k));
+        for (int e = t; e < NT * (kKC / 4); e += kM) {
+            const int kc = e / NT, r = e - kc * NT;
+            store_split4(Bhi, Blo, NT, r, kc, load4<VEC4>(Bt, n0 + r, (long)n0 + nvalid, ldb, kb + kc * 4, k));
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < kKC / 8; ++ks) {
+                const uint64_t ah = make_desc(smem_u32(Ahi) + ks * 2 * kM * 16, kM * 16, 128);
+                const uint64_t al = make_desc(smem_u32(Alo) + ks * 2 * kM * 16, kM * 16, 128);
+                const uint64_t bh = make_desc(smem_u32(Bhi) + ks * 2 * NT * 16, NT * 16, 128);
+                const uint64_t bl = make_desc(smem_u32(Blo) + ks * 2 * NT * 16, NT * 16, 128);
+                mma_tf32(tmem, ah, bh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                mma_tf32(tmem, ah, bl, idesc, 1);
+                mma_tf32(tmem, al, bh, idesc, 1);
+            }
+            mma_commit(&bar);
+        }
+        // the operand buffers are rewritten by the next chunk: wait until the tensor core has consumed them
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+    }
+
+    // ---- epilogue: TMEM row -> shared-memory panel (64 columns at a time) -> coalesced global stores
+    constexpr int PANEL = NT < 64 ? NT : 64, PP = PANEL + 4;
+    float *stage = smem;                                          // 128 x (PANEL+4) floats <= operand buffers
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    for (int p0 = 0; p0 < NT; p0 += PANEL) {
+#pragma unroll
+        for (int c0 = 0; c0 < PANEL; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + lane_sel + p0 + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4 *>(stage + t * PP + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        __syncthreads();
+        constexpr int CPR = PANEL / 4;                            // float4 chunks per row
+        for (int e = t; e < kM * CPR; e += kM) {
+            const int r = e / CPR, c = (e - r * CPR) * 4;
+            const long grow = row0 + r;
+            const int gcol = n0 + p0 + c;
+            if (grow < rows && gcol < n) {
+                const float4 v = *reinterpret_cast<const float4 *>(stage + r * PP + c);
+                float *dst = C + grow * ldc + gcol;
+                if (gcol + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                    *reinterpret_cast<float4 *>(dst) = v;
+                } else {
+                    dst[0] = v.x;
+                    if (gcol + 1 < n) dst[1] = v.y;
+                    if (gcol + 2 < n) dst[2] = v.z;
+                    if (gcol + 3 < n) dst[3] = v.w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols(NT)) : "memory");
+}
+
+template <int NT>
+int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb, float *C, long ldc,
+           cudaStream_t st) {
+    const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(Bt) & 15u) == 0);
+    size_t smem = sizeof(float) * (size_t)(2 * kM * kKC + 2 * NT * kKC);
+    const size_t stage = sizeof(float) * (size_t)kM * ((NT < 64 ? NT : 64) + 4);
+    if (stage > smem) smem = stage;
+    dim3 grid((unsigned)((rows + kM - 1) / kM), (unsigned)((n + NT - 1) / NT));
+    cudaError_t e;
+    if (vec) {
+        auto kern = gemm_rows_kernel<NT, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, kM, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
+    } else {
+        auto kern = gemm_rows_kernel<NT, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, kM, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
+    }
+    return pasnl_launch_status();
+}
+
+}  // namespace gtc
+
+extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb,
+                                      float *C, long ldc, void *stream) {
+    PASNL_CHECK_ARG(rows >= 0 && k >= 1 && n >= 1 && lda >= k && ldb >= k && ldc >= n);
+    if (rows == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(A && Bt && C && rows / 128 < 2147483647L && n <= 256 * 65535);
+    cudaStream_t st = (cudaStream_t)stream;
+    // UMMA N must be a multiple of 16 (M = 128): the tile is padded in shared memory, stores are bounds-checked
+    if (n <= 32) return gtc::launch<32>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
+    if (n <= 64) return gtc::launch<64>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
+    if (n <= 128) return gtc::launch<128>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
+    return gtc::launch<256>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
+}

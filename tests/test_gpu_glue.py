@@ -63,3 +63,25 @@ def test_tf_util_layers_take_the_fused_path_and_match_op_by_op(cuda):
         finally:
             tf_util._fused_dense_bn = orig
     torch.testing.assert_close(fused, plain, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,k,n", [(4096, 64, 64), (16384, 128, 128), (5000, 134, 128), (8192, 9, 64), (2048, 3, 32),
+                                      (1024, 2048, 128), (4096, 259, 256), (3000, 512, 1024), (777, 70, 48), (600, 131, 40)])
+def test_tcgen05_gemm_rows_is_fp32_accurate(cuda, rows, k, n):
+    """C = A.Bt^T through pasnl_gemm_rows_tf32x3 (3xTF32 on tcgen05) against fp64, held to the same 1e-4 bar as the
+    rest of the path; a plain single-pass TF32 product would miss it by ~10x."""
+    from pointasnl_b200 import _ops
+    torch.manual_seed(rows + k + n)
+    a = torch.randn(rows, k, device=cuda) * 2.0 + 0.5
+    bt = torch.randn(n, k, device=cuda)
+    got = _ops.gemm_rows(a, bt)
+    want = a.double() @ bt.double().t()
+    scale = float(want.abs().max())
+    err = float((got.double() - want).abs().max())
+    assert err <= 2e-6 * scale * max(1.0, (k / 64) ** 0.5) + 1e-6, (err, scale)
+    ref32 = float((torch.mm(a, bt.t()).double() - want).abs().max())      # what cuBLAS fp32 itself achieves
+    assert err <= 8 * ref32 + 1e-6 * scale
+    # strided operands (a column slice of a wider tensor)
+    wide = torch.randn(rows, k + 8, device=cuda)
+    got2 = _ops.gemm_rows(wide[:, 4:4 + k], bt)
+    torch.testing.assert_close(got2.double(), wide[:, 4:4 + k].double() @ bt.double().t(), rtol=1e-4, atol=1e-4 * scale)
