@@ -364,7 +364,10 @@ class NLCore(torch.autograd.Function):
 # ------------------------------------------------------------------ dense glue: GEMM + fused BN/activation epilogue
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
+import os as _os
+
 GEMM_MIN_ROWS = 512   # below this a 128-row tile grid cannot fill the GPU: cuBLAS takes those (fc layers, rows = batch)
+GEMM_IMPL = _os.environ.get("PASNL_GEMM", "tc")   # "tc" = tcgen05 3xTF32 kernel, "cublas" = torch.mm (fp32 SIMT)
 
 
 def gemm_rows(a, bt):
@@ -372,7 +375,7 @@ def gemm_rows(a, bt):
     tall enough, cuBLAS otherwise.  Both operands row-major with a unit inner stride."""
     rows, k = a.shape
     n = bt.shape[0]
-    if rows < GEMM_MIN_ROWS or not a.is_cuda:
+    if rows < GEMM_MIN_ROWS or not a.is_cuda or GEMM_IMPL != "tc":
         return torch.mm(a, bt.t())
     if a.stride(1) != 1:
         a = a.contiguous()

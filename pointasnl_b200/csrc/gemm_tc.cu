@@ -5,16 +5,16 @@
 // This is the shape of every 1x1-conv / fully-connected layer around the point-set ops:
 // forward y = x.W (Bt = W^T), input gradient dx = dy.W^T (Bt = W).  rows = B*S*K is 10^4..10^6, k and n are 3..4096.
 // cuBLAS runs these as fp32 SIMT SGEMMs (~50 TFLOP/s, 5.5 ms of a 11.5 ms cls step); a single TF32 pass would break the
-// 1e-4 parity bar, so each product is split a = a_hi + a_lo (tf32 round-to-nearest) and accumulated as
+// 1e-4 parity bar, so each product is split a = a_hi + a_lo (a_hi = a truncated to TF32) and accumulated as
 // a_hi.b_hi + a_hi.b_lo + a_lo.b_hi in fp32 TMEM (error ~2^-21 relative).  At 3 MMAs per k-step the tensor pipe still
 // outruns HBM for these skinny shapes, so the kernel is memory bound: bytes = 4*rows*(k+n).
 //
-// CTA = 128 threads = one 128-row x NT-column output tile; k is consumed in 32-wide chunks:
+// CTA = 256 threads = one 128-row x NT-column output tile; k is consumed in 32-wide chunks through TWO operand stages:
 //   all threads load + split the A (128 x 32) and Bt (NT x 32) chunks into the canonical no-swizzle K-major UMMA
-//   layout [k/4][row][4] (hi and lo copies), one thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT),
-//   tcgen05.commit -> mbarrier; after the last chunk every thread tcgen05.ld's its row and the tile leaves through a
-//   shared-memory transpose so that global stores are coalesced.  Latency is hidden by co-resident CTAs (64-96 KB of
-//   shared memory, 32..256 TMEM columns each), not by an intra-CTA pipeline, in this revision.
+//   layout [k/4][row][4] (hi and lo copies); one thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT) and a
+//   tcgen05.commit to the stage's mbarrier; the MMAs run asynchronously while the CTA loads the next chunk into the
+//   other stage (a stage is rewritten only after its commit has arrived).  After the last chunk the accumulator rows
+//   leave TMEM through a shared-memory panel so that global stores are coalesced.
 #include "common.cuh"
 
 using namespace pasnl;
@@ -24,11 +24,7 @@ namespace gtc {
 constexpr int kM = 128;
 constexpr int kKC = 32;     // k chunk
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
@@ -90,9 +86,12 @@ __device__ __forceinline__ float4 load4(const float *__restrict__ base, long row
     return x;
 }
 __device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int row, int kc, float4 x) {
+    // hi = x with the 13 low mantissa bits cleared (exactly a TF32 value), lo = x - hi (exact in fp32, |lo| < 2^-10 |x|).
+    // One LOP + one FADD per element: the F2F conversions (cvt.rna.tf32) run on the 16-lane XU pipe and were the
+    // bottleneck of the first revision.  The tensor core drops lo's bits below TF32: 2^-20 relative to x.
     float4 h, l;
-    h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-    l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+    h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
     const int o = (kc * rows + row) * 4;
     *reinterpret_cast<float4 *>(hi + o) = h;
     *reinterpret_cast<float4 *>(lo + o) = l;
@@ -100,14 +99,15 @@ __device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int
 
 constexpr int tmem_cols(int nt) { return nt < 32 ? 32 : nt; }   // power of two >= 32 (NT is 32/64/128/256)
 
+constexpr int kThreads = 256;   // 8 warps: all load/split; warp w reads TMEM lanes 32*(w%4).. in the epilogue
+
 template <int NT, bool VEC4>
-__global__ void __launch_bounds__(kM) gemm_rows_kernel(long rows, int k, int n, const float *__restrict__ A, long lda,
-                                                       const float *__restrict__ Bt, long ldb, float *__restrict__ C,
-                                                       long ldc) {
+__global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, int n, const float *__restrict__ A,
+                                                             long lda, const float *__restrict__ Bt, long ldb,
+                                                             float *__restrict__ C, long ldc) {
+    constexpr int kStage = 2 * kM * kKC + 2 * NT * kKC;            // floats per operand stage (A hi/lo, B hi/lo)
     extern __shared__ __align__(128) float smem[];
-    float *Ahi = smem, *Alo = Ahi + kM * kKC;                     // [8][128][4]
-    float *Bhi = Alo + kM * kKC, *Blo = Bhi + NT * kKC;           // [8][NT][4]
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];                                    // "stage s has been consumed by the tensor core"
     __shared__ uint32_t tmem_slot;
 
     const int t = threadIdx.x, warp = t >> 5;
@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(kM) gemm_rows_kernel(long rows, int k, int n, 
     const int nvalid = min(NT, n - n0);
 
     if (t == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -131,15 +132,42 @@ __global__ void __launch_bounds__(kM) gemm_rows_kernel(long rows, int k, int n, 
     const uint32_t tmem = tmem_slot;
     constexpr uint32_t idesc = make_idesc(kM, NT);
 
-    uint32_t phase = 0;
-    for (int kb = 0; kb < k; kb += kKC) {
-        // ---- load + split this k-chunk of A (128 rows) and Bt (NT rows)
+    // Software pipeline over 32-wide k-chunks with two operand stages: while the tensor core consumes stage s
+    // (asynchronously -- nobody waits for the MMAs of chunk i before loading chunk i+1), all 256 threads load and
+    // split the next chunk into stage s^1.  A stage is only rewritten after the commit of the MMAs that read it.
+    const int nchunks = (k + kKC - 1) / kKC;
+    uint32_t ph0 = 0, ph1 = 0;
+    for (int i = 0; i < nchunks; ++i) {
+        const int sidx = i & 1;
+        float *Ahi = smem + sidx * kStage, *Alo = Ahi + kM * kKC;                 // [8][128][4]
+        float *Bhi = Alo + kM * kKC, *Blo = Bhi + NT * kKC;                        // [8][NT][4]
+        const int kb = i * kKC;
+        if (i >= 2) {
+            if (sidx == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+            else           { mbar_wait(&bar[1], ph1); ph1 ^= 1u; }
+        }
+        // issue all global loads of this thread first (4 for A, NT/32 for Bt), then split + store
+        float4 av[(kM * (kKC / 4)) / kThreads];
 #pragma unroll
-        for (int kc = 0; kc < kKC / 4; ++kc)
-            store_split4(Ahi, Alo, kM, t, kc, load4<VEC4>(A, row0 + t, rows, lda, kb + kc * 4, k));
-        for (int e = t; e < NT * (kKC / 4); e += kM) {
-            const int kc = e / NT, r = e - kc * NT;
-            store_split4(Bhi, Blo, NT, r, kc, load4<VEC4>(Bt, n0 + r, (long)n0 + nvalid, ldb, kb + kc * 4, k));
+        for (int j = 0; j < (kM * (kKC / 4)) / kThreads; ++j) {
+            const int e = t + j * kThreads, kc = e / kM, r = e - kc * kM;
+            av[j] = load4<VEC4>(A, row0 + r, rows, lda, kb + kc * 4, k);
+        }
+        float4 bv[(NT * (kKC / 4)) / kThreads];
+#pragma unroll
+        for (int j = 0; j < (NT * (kKC / 4)) / kThreads; ++j) {
+            const int e = t + j * kThreads, kc = e / NT, r = e - kc * NT;
+            bv[j] = load4<VEC4>(Bt, n0 + r, (long)n0 + nvalid, ldb, kb + kc * 4, k);
+        }
+#pragma unroll
+        for (int j = 0; j < (kM * (kKC / 4)) / kThreads; ++j) {
+            const int e = t + j * kThreads, kc = e / kM, r = e - kc * kM;
+            store_split4(Ahi, Alo, kM, r, kc, av[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < (NT * (kKC / 4)) / kThreads; ++j) {
+            const int e = t + j * kThreads, kc = e / NT, r = e - kc * NT;
+            store_split4(Bhi, Blo, NT, r, kc, bv[j]);
         }
         fence_async_smem();
         tc_fence_before();
@@ -152,34 +180,36 @@ __global__ void __launch_bounds__(kM) gemm_rows_kernel(long rows, int k, int n, 
                 const uint64_t al = make_desc(smem_u32(Alo) + ks * 2 * kM * 16, kM * 16, 128);
                 const uint64_t bh = make_desc(smem_u32(Bhi) + ks * 2 * NT * 16, NT * 16, 128);
                 const uint64_t bl = make_desc(smem_u32(Blo) + ks * 2 * NT * 16, NT * 16, 128);
-                mma_tf32(tmem, ah, bh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                mma_tf32(tmem, ah, bh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
                 mma_tf32(tmem, ah, bl, idesc, 1);
                 mma_tf32(tmem, al, bh, idesc, 1);
             }
-            mma_commit(&bar);
+            mma_commit(&bar[sidx]);
         }
-        // the operand buffers are rewritten by the next chunk: wait until the tensor core has consumed them
-        mbar_wait(&bar, phase);
-        phase ^= 1u;
-        tc_fence_after();
     }
+    // the last commit completes after every earlier MMA of this thread: one wait covers the whole accumulator
+    if (((nchunks - 1) & 1) == 0) mbar_wait(&bar[0], ph0);
+    else mbar_wait(&bar[1], ph1);
+    tc_fence_after();
 
-    // ---- epilogue: TMEM row -> shared-memory panel (64 columns at a time) -> coalesced global stores
+    // ---- epilogue: TMEM rows -> shared-memory panel (<= 64 columns at a time) -> coalesced global stores.
+    // warps w and w+4 share TMEM lanes 32*(w%4)..; with a 64-column panel each takes one 32-column half.
     constexpr int PANEL = NT < 64 ? NT : 64, PP = PANEL + 4;
-    float *stage = smem;                                          // 128 x (PANEL+4) floats <= operand buffers
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    float *stage = smem;                                          // 128 x (PANEL+4) floats, inside operand stage 0
+    const int lrow = (warp & 3) * 32 + (t & 31);                  // the accumulator row this thread can read
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     for (int p0 = 0; p0 < NT; p0 += PANEL) {
-#pragma unroll
-        for (int c0 = 0; c0 < PANEL; c0 += 32) {
+        const int c0 = (warp >> 2) * 32;
+        if (c0 < PANEL) {
             float v[32];
             tmem_ld32(tmem + lane_sel + p0 + c0, v);
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4 *>(stage + t * PP + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                *reinterpret_cast<float4 *>(stage + lrow * PP + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         __syncthreads();
         constexpr int CPR = PANEL / 4;                            // float4 chunks per row
-        for (int e = t; e < kM * CPR; e += kM) {
+        for (int e = t; e < kM * CPR; e += kThreads) {
             const int r = e / CPR, c = (e - r * CPR) * 4;
             const long grow = row0 + r;
             const int gcol = n0 + p0 + c;
@@ -209,21 +239,19 @@ int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, l
            cudaStream_t st) {
     const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(Bt) & 15u) == 0);
-    size_t smem = sizeof(float) * (size_t)(2 * kM * kKC + 2 * NT * kKC);
-    const size_t stage = sizeof(float) * (size_t)kM * ((NT < 64 ? NT : 64) + 4);
-    if (stage > smem) smem = stage;
+    const size_t smem = sizeof(float) * 2 * (size_t)(2 * kM * kKC + 2 * NT * kKC);   // two operand stages
     dim3 grid((unsigned)((rows + kM - 1) / kM), (unsigned)((n + NT - 1) / NT));
     cudaError_t e;
     if (vec) {
         auto kern = gemm_rows_kernel<NT, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, kM, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
+        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
     } else {
         auto kern = gemm_rows_kernel<NT, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, kM, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
+        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
     }
     return pasnl_launch_status();
 }

@@ -3,7 +3,7 @@
 // Same contract as nl_fwd_kernel in nonlocal.cu (reference utils/pointasnl_util.py:195-212): out = softmax(Q Kf^T * scale) V
 // without materialising the (S x N) map, plus the row log-sum-exp for the backward.  The parity bar is 1e-4 relative
 // against the fp32 reference, which a single TF32 pass (10-bit mantissa) misses by ~10x, so every product is a
-// 3xTF32 split:  a = a_hi + a_lo (a_hi = rna(tf32), a_lo = rna(a - a_hi)),  a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi
+// 3xTF32 split:  a = a_hi + a_lo (a_hi = a truncated to TF32, a_lo = a - a_hi),  a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi
 // (the dropped a_lo.b_lo term is 2^-22 relative).  Three tcgen05.mma.kind::tf32 per k-step, fp32 accumulation in TMEM.
 //
 // One CTA = 128 threads = 128 query rows (UMMA M = 128: TMEM lane i holds row i, so thread i owns query row i and the
@@ -27,11 +27,7 @@ constexpr int kBN = 64;     // keys per tile (UMMA N of the S product, K extent 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -83,9 +79,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // write x (split into hi / lo) at operand position (row, k) of a [k/4][rows][4] tile pair
 __device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int row, int kc, float4 x) {
+    // hi = x with the 13 low mantissa bits cleared (exactly a TF32 value), lo = x - hi (exact in fp32, |lo| < 2^-10 |x|).
+    // One LOP + one FADD per element: the F2F conversions (cvt.rna.tf32) run on the 16-lane XU pipe and were the
+    // bottleneck of the first revision.  The tensor core drops lo's bits below TF32: 2^-20 relative to x.
     float4 h, l;
-    h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-    l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+    h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
     const int o = (kc * rows + row) * 4;
     *reinterpret_cast<float4 *>(hi + o) = h;
     *reinterpret_cast<float4 *>(lo + o) = l;
@@ -162,10 +161,10 @@ __global__ void __launch_bounds__(kM) nl_fwd_tc_kernel(int s, int n, const float
                 const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float h = tf32_rna(vv[i]);
+                    const float h = tf32_hi(vv[i]);
                     const int o = ((key >> 2) * D + (kc * 4 + i)) * 4 + (key & 3);
                     Vhi[o] = h;
-                    Vlo[o] = tf32_rna(vv[i] - h);
+                    Vlo[o] = vv[i] - h;
                 }
             }
         }
