@@ -11,7 +11,7 @@
 //
 // CTA = 256 threads = one 128-row x NT-column output tile; k is consumed in 32-wide chunks through TWO operand stages:
 //   all threads load + split the A (128 x 32) and Bt (NT x 32) chunks into the canonical no-swizzle K-major UMMA
-//   layout [k/4][row][4] (hi and lo copies); one thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT) and a
+//   layout [row/8][k/4][row%8][4] (hi and lo copies); one thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT) and a
 //   tcgen05.commit to the stage's mbarrier; the MMAs run asynchronously while the CTA loads the next chunk into the
 //   other stage (a stage is rewritten only after its commit has arrived).  After the last chunk the accumulator rows
 //   leave TMEM through a shared-memory panel so that global stores are coalesced.
@@ -97,6 +97,44 @@ __device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int
     *reinterpret_cast<float4 *>(lo + o) = l;
 }
 
+// Operand tile layout (canonical no-swizzle K-major, row-group major):  [row/8][kc = k/4][row%8][4 floats]
+//   core matrix = 8 rows x 16 bytes (128 contiguous bytes); LBO (next core matrix along k) = 128 bytes;
+//   SBO (next 8-row group) = (kKC/4) * 128 bytes.
+// A warp fills 8 rows x 4 k-chunks per instruction: lane = (row%8) + 8*(kc%4).  Global side: 8 rows x 64 contiguous
+// bytes (8 L1 tags, 16 sectors) instead of 32 different rows; shared side: 4 x 128 contiguous bytes, conflict free.
+constexpr int kSBO = (kKC / 4) * 128;   // bytes
+__device__ __forceinline__ int tile_off(int row, int kc) { return ((row >> 3) * (kKC / 4) + kc) * 32 + (row & 7) * 4; }
+
+template <int ROWS, bool VEC4>
+__device__ __forceinline__ void load_tile(float *hi, float *lo, const float *__restrict__ src, long row_base,
+                                          long row_limit, long ld, int kb, int k, int warp, int lane) {
+    constexpr int ITEMS = (ROWS / 8) * 2;                // (row group, k half) pairs, 32 float4 each
+    constexpr int PER_WARP = (ITEMS + 7) / 8;
+    const int r8 = lane & 7, kq = lane >> 3;
+    float4 v[PER_WARP];
+#pragma unroll
+    for (int j = 0; j < PER_WARP; ++j) {
+        const int item = warp + 8 * j;
+        const int rg = item % (ROWS / 8), h = item / (ROWS / 8);
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < ITEMS) v[j] = load4<VEC4>(src, row_base + rg * 8 + r8, row_limit, ld, kb + (kq + 4 * h) * 4, k);
+    }
+#pragma unroll
+    for (int j = 0; j < PER_WARP; ++j) {
+        const int item = warp + 8 * j;
+        const int rg = item % (ROWS / 8), h = item / (ROWS / 8);
+        if (item < ITEMS) {
+            const float4 x = v[j];
+            float4 hh, ll;
+            hh.x = tf32_hi(x.x); hh.y = tf32_hi(x.y); hh.z = tf32_hi(x.z); hh.w = tf32_hi(x.w);
+            ll.x = x.x - hh.x; ll.y = x.y - hh.y; ll.z = x.z - hh.z; ll.w = x.w - hh.w;
+            const int o = tile_off(rg * 8 + r8, kq + 4 * h);
+            *reinterpret_cast<float4 *>(hi + o) = hh;
+            *reinterpret_cast<float4 *>(lo + o) = ll;
+        }
+    }
+}
+
 constexpr int tmem_cols(int nt) { return nt < 32 ? 32 : nt; }   // power of two >= 32 (NT is 32/64/128/256)
 
 constexpr int kThreads = 256;   // 8 warps: all load/split; warp w reads TMEM lanes 32*(w%4).. in the epilogue
@@ -146,29 +184,9 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
             if (sidx == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
             else           { mbar_wait(&bar[1], ph1); ph1 ^= 1u; }
         }
-        // issue all global loads of this thread first (4 for A, NT/32 for Bt), then split + store
-        float4 av[(kM * (kKC / 4)) / kThreads];
-#pragma unroll
-        for (int j = 0; j < (kM * (kKC / 4)) / kThreads; ++j) {
-            const int e = t + j * kThreads, kc = e / kM, r = e - kc * kM;
-            av[j] = load4<VEC4>(A, row0 + r, rows, lda, kb + kc * 4, k);
-        }
-        float4 bv[(NT * (kKC / 4)) / kThreads];
-#pragma unroll
-        for (int j = 0; j < (NT * (kKC / 4)) / kThreads; ++j) {
-            const int e = t + j * kThreads, kc = e / NT, r = e - kc * NT;
-            bv[j] = load4<VEC4>(Bt, n0 + r, (long)n0 + nvalid, ldb, kb + kc * 4, k);
-        }
-#pragma unroll
-        for (int j = 0; j < (kM * (kKC / 4)) / kThreads; ++j) {
-            const int e = t + j * kThreads, kc = e / kM, r = e - kc * kM;
-            store_split4(Ahi, Alo, kM, r, kc, av[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < (NT * (kKC / 4)) / kThreads; ++j) {
-            const int e = t + j * kThreads, kc = e / NT, r = e - kc * NT;
-            store_split4(Bhi, Blo, NT, r, kc, bv[j]);
-        }
+        // hi = a & mask, lo = a - hi.  The split costs one LOP + one FADD per element (no F2F conversions).
+        load_tile<kM, VEC4>(Ahi, Alo, A, row0, rows, lda, kb, k, warp, t & 31);
+        load_tile<NT, VEC4>(Bhi, Blo, Bt, n0, (long)n0 + nvalid, ldb, kb, k, warp, t & 31);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -176,10 +194,10 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < kKC / 8; ++ks) {
-                const uint64_t ah = make_desc(smem_u32(Ahi) + ks * 2 * kM * 16, kM * 16, 128);
-                const uint64_t al = make_desc(smem_u32(Alo) + ks * 2 * kM * 16, kM * 16, 128);
-                const uint64_t bh = make_desc(smem_u32(Bhi) + ks * 2 * NT * 16, NT * 16, 128);
-                const uint64_t bl = make_desc(smem_u32(Blo) + ks * 2 * NT * 16, NT * 16, 128);
+                const uint64_t ah = make_desc(smem_u32(Ahi) + ks * 256, 128, kSBO);
+                const uint64_t al = make_desc(smem_u32(Alo) + ks * 256, 128, kSBO);
+                const uint64_t bh = make_desc(smem_u32(Bhi) + ks * 256, 128, kSBO);
+                const uint64_t bl = make_desc(smem_u32(Blo) + ks * 256, 128, kSBO);
                 mma_tf32(tmem, ah, bh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
                 mma_tf32(tmem, ah, bl, idesc, 1);
                 mma_tf32(tmem, al, bh, idesc, 1);

@@ -9,8 +9,8 @@
 // One CTA = 128 threads = 128 query rows (UMMA M = 128: TMEM lane i holds row i, so thread i owns query row i and the
 // softmax is thread-local: no shuffles).  Per 64-key tile:
 //   1. all threads load the K / V rows from global, split them, and write the four B operands to shared memory in the
-//      canonical no-swizzle K-major UMMA layout  [k/4][row][4 floats]  (core matrix = 8 rows x 16 bytes, LBO = rows*16,
-//      SBO = 128);
+//      canonical no-swizzle K-major UMMA layout  [row/8][k/4][row%8][4 floats]  (core matrix = 8 rows x 16 bytes,
+//      LBO = 128, SBO = (k/4)*128), filled by warps with coalesced global reads;
 //   2. one thread issues S = Q.K^T (3 MMAs per 8-wide k-step) into TMEM columns [0,64), tcgen05.commit -> mbarrier;
 //   3. every thread tcgen05.ld's its row of S, does the online-softmax update, writes P (hi/lo) as the next A operand;
 //   4. one thread issues PV = P.V into TMEM columns [64, 64+D); every thread adds its PV row into the fp32 output row it
@@ -77,15 +77,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// write x (split into hi / lo) at operand position (row, k) of a [k/4][rows][4] tile pair
-__device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int row, int kc, float4 x) {
+// Operand tiles use the canonical no-swizzle K-major layout, row-group major: [row/8][kc = k/4][row%8][4 floats]
+// (core matrix = 8 rows x 16 B; LBO = 128 B to the next k core matrix, SBO = KCH*128 B to the next 8-row group, KCH =
+// k-chunks per row).  A warp can then fill 8 rows x 4 k-chunks from 8 x 64 contiguous global bytes without conflicts.
+__device__ __forceinline__ int tile_off(int kch, int row, int kc) { return ((row >> 3) * kch + kc) * 32 + (row & 7) * 4; }
+
+// write x (split into hi / lo) at operand position (row, kc) of a tile pair with KCH k-chunks per row
+__device__ __forceinline__ void store_split4(float *hi, float *lo, int kch, int row, int kc, float4 x) {
     // hi = x with the 13 low mantissa bits cleared (exactly a TF32 value), lo = x - hi (exact in fp32, |lo| < 2^-10 |x|).
     // One LOP + one FADD per element: the F2F conversions (cvt.rna.tf32) run on the 16-lane XU pipe and were the
     // bottleneck of the first revision.  The tensor core drops lo's bits below TF32: 2^-20 relative to x.
     float4 h, l;
     h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
     l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-    const int o = (kc * rows + row) * 4;
+    const int o = tile_off(kch, row, kc);
     *reinterpret_cast<float4 *>(hi + o) = h;
     *reinterpret_cast<float4 *>(lo + o) = l;
 }
@@ -95,10 +100,10 @@ __global__ void __launch_bounds__(kM) nl_fwd_tc_kernel(int s, int n, const float
                                                        const float *__restrict__ kv, float scale_log2,
                                                        float *__restrict__ out, float *__restrict__ lse) {
     extern __shared__ __align__(128) float smem[];
-    float *Qhi = smem, *Qlo = Qhi + kM * D;                 // A of S:  [D/4][128][4]
-    float *Khi = Qlo + kM * D, *Klo = Khi + kBN * D;        // B of S:  [D/4][64][4]
-    float *Vhi = Klo + kBN * D, *Vlo = Vhi + kBN * D;       // B of PV: [64/4][D][4]   (N = D rows, K = keys)
-    float *Phi = Vlo + kBN * D, *Plo = Phi + kM * kBN;      // A of PV: [64/4][128][4]
+    float *Qhi = smem, *Qlo = Qhi + kM * D;                 // A of S:  128 rows x D
+    float *Khi = Qlo + kM * D, *Klo = Khi + kBN * D;        // B of S:  64 rows (keys) x D
+    float *Vhi = Klo + kBN * D, *Vlo = Vhi + kBN * D;       // B of PV: D rows (channels) x 64 (keys)
+    float *Phi = Vlo + kBN * D, *Plo = Phi + kM * kBN;      // A of PV: 128 rows x 64 (keys)
     __shared__ uint64_t bar_s, bar_pv;
     __shared__ uint32_t tmem_base_slot;
 
@@ -119,12 +124,17 @@ __global__ void __launch_bounds__(kM) nl_fwd_tc_kernel(int s, int n, const float
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // Q tile: thread t owns row t (zero rows past s)
-#pragma unroll
-    for (int kc = 0; kc < D / 4; ++kc) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < s) x = __ldg(reinterpret_cast<const float4 *>(qb + (size_t)row * D + kc * 4));
-        store_split4(Qhi, Qlo, kM, t, kc, x);
+    // Q tile (128 rows x D): warp-coalesced, lane = (row%8) + 8*(kc%4); zero rows past s
+    {
+        const int lane = t & 31, r8 = lane & 7, kq = lane >> 3;
+        constexpr int ITEMS = (kM / 8) * (D / 16);
+        for (int item = warp; item < ITEMS; item += 4) {
+            const int rg = item % (kM / 8), h = item / (kM / 8);
+            const int r = rg * 8 + r8, kc = kq + 4 * h;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < s) x = __ldg(reinterpret_cast<const float4 *>(qb + (size_t)(row0 + r) * D + kc * 4));
+            store_split4(Qhi, Qlo, D / 4, r, kc, x);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -144,27 +154,30 @@ __global__ void __launch_bounds__(kM) nl_fwd_tc_kernel(int s, int n, const float
 
     for (int col0 = 0; col0 < n; col0 += kBN) {
         const int cv = min(kBN, n - col0);
-        // ---- 1. K / V tile -> split -> operand layouts.  64 keys x D: 128 threads, thread = (key = t % 64, half = t / 64)
+        // ---- 1. K / V tile -> split -> operand layouts (64 keys x D each), warp-coalesced like the Q tile
         {
-            const int key = t & (kBN - 1), half = t >> 6;
-            const float *kr = kvb + (size_t)(col0 + key) * 2 * D;
-            const bool ok = key < cv;
+            const int lane = t & 31, r8 = lane & 7, kq = lane >> 3;
+            constexpr int ITEMS = (kBN / 8) * (D / 16);
 #pragma unroll
-            for (int kc = half; kc < D / 4; kc += 2) {
+            for (int j = 0; j < ITEMS / 4; ++j) {
+                const int item = warp + 4 * j;
+                const int rg = item % (kBN / 8), h = item / (kBN / 8);
+                const int key = rg * 8 + r8, kc = kq + 4 * h;
                 float4 xk = make_float4(0.f, 0.f, 0.f, 0.f), xv = xk;
-                if (ok) {
-                    xk = __ldg(reinterpret_cast<const float4 *>(kr + kc * 4));
-                    xv = __ldg(reinterpret_cast<const float4 *>(kr + D + kc * 4));
+                if (key < cv) {
+                    const float *kr = kvb + (size_t)(col0 + key) * 2 * D + kc * 4;
+                    xk = __ldg(reinterpret_cast<const float4 *>(kr));
+                    xv = __ldg(reinterpret_cast<const float4 *>(kr + D));
                 }
-                store_split4(Khi, Klo, kBN, key, kc, xk);
-                // V as B operand of PV: element (n = d, k = key) at [(key/4)][d][key%4]
+                store_split4(Khi, Klo, D / 4, key, kc, xk);
+                // V is the B operand of PV: rows = d (N), k = key -> element (d, key) at tile_off(16, d, key/4) + key%4
                 const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float h = tf32_hi(vv[i]);
-                    const int o = ((key >> 2) * D + (kc * 4 + i)) * 4 + (key & 3);
-                    Vhi[o] = h;
-                    Vlo[o] = vv[i] - h;
+                    const float hh = tf32_hi(vv[i]);
+                    const int o = tile_off(kBN / 4, kc * 4 + i, key >> 2) + (key & 3);
+                    Vhi[o] = hh;
+                    Vlo[o] = vv[i] - hh;
                 }
             }
         }
@@ -176,10 +189,10 @@ __global__ void __launch_bounds__(kM) nl_fwd_tc_kernel(int s, int n, const float
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < D / 8; ++ks) {
-                const uint64_t ah = make_desc(smem_u32(Qhi) + ks * 2 * kM * 16, kM * 16, 128);
-                const uint64_t al = make_desc(smem_u32(Qlo) + ks * 2 * kM * 16, kM * 16, 128);
-                const uint64_t bh = make_desc(smem_u32(Khi) + ks * 2 * kBN * 16, kBN * 16, 128);
-                const uint64_t bl = make_desc(smem_u32(Klo) + ks * 2 * kBN * 16, kBN * 16, 128);
+                const uint64_t ah = make_desc(smem_u32(Qhi) + ks * 256, 128, (D / 4) * 128);
+                const uint64_t al = make_desc(smem_u32(Qlo) + ks * 256, 128, (D / 4) * 128);
+                const uint64_t bh = make_desc(smem_u32(Khi) + ks * 256, 128, (D / 4) * 128);
+                const uint64_t bl = make_desc(smem_u32(Klo) + ks * 256, 128, (D / 4) * 128);
                 mma_tf32(tmem_s, ah, bh, idesc_s, ks > 0);
                 mma_tf32(tmem_s, ah, bl, idesc_s, 1);
                 mma_tf32(tmem_s, al, bh, idesc_s, 1);
@@ -218,7 +231,7 @@ __global__ void __launch_bounds__(kM) nl_fwd_tc_kernel(int s, int n, const float
         m_run = m_new;
 #pragma unroll
         for (int kc = 0; kc < kBN / 4; ++kc)
-            store_split4(Phi, Plo, kM, t, kc, make_float4(sv[kc * 4], sv[kc * 4 + 1], sv[kc * 4 + 2], sv[kc * 4 + 3]));
+            store_split4(Phi, Plo, kBN / 4, t, kc, make_float4(sv[kc * 4], sv[kc * 4 + 1], sv[kc * 4 + 2], sv[kc * 4 + 3]));
 #pragma unroll
         for (int c = 0; c < D; ++c) o_acc[c] *= alpha;
         fence_async_smem();
@@ -229,10 +242,10 @@ __global__ void __launch_bounds__(kM) nl_fwd_tc_kernel(int s, int n, const float
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < kBN / 8; ++ks) {
-                const uint64_t ah = make_desc(smem_u32(Phi) + ks * 2 * kM * 16, kM * 16, 128);
-                const uint64_t al = make_desc(smem_u32(Plo) + ks * 2 * kM * 16, kM * 16, 128);
-                const uint64_t bh = make_desc(smem_u32(Vhi) + ks * 2 * D * 16, D * 16, 128);
-                const uint64_t bl = make_desc(smem_u32(Vlo) + ks * 2 * D * 16, D * 16, 128);
+                const uint64_t ah = make_desc(smem_u32(Phi) + ks * 256, 128, (kBN / 4) * 128);
+                const uint64_t al = make_desc(smem_u32(Plo) + ks * 256, 128, (kBN / 4) * 128);
+                const uint64_t bh = make_desc(smem_u32(Vhi) + ks * 256, 128, (kBN / 4) * 128);
+                const uint64_t bl = make_desc(smem_u32(Vlo) + ks * 256, 128, (kBN / 4) * 128);
                 mma_tf32(tmem_pv, ah, bh, idesc_pv, ks > 0);
                 mma_tf32(tmem_pv, ah, bl, idesc_pv, 1);
                 mma_tf32(tmem_pv, al, bh, idesc_pv, 1);
