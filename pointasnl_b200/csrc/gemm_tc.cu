@@ -9,9 +9,9 @@
 // a_hi.b_hi + a_hi.b_lo + a_lo.b_hi in fp32 TMEM (error ~2^-21 relative).  At 3 MMAs per k-step the tensor pipe still
 // outruns HBM for these skinny shapes, so the kernel is memory bound: bytes = 4*rows*(k+n).
 //
-// CTA = 256 threads = one 128-row x NT-column output tile; k is consumed in 32-wide chunks through TWO operand stages:
-//   all threads load + split the A (128 x 32) and Bt (NT x 32) chunks into the canonical no-swizzle K-major UMMA
-//   layout [row/8][k/4][row%8][4] (hi and lo copies); one thread issues 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT) and a
+// CTA = 256 threads = one 128-row x NT-column output tile; k is consumed in 16-wide chunks through TWO operand stages:
+//   all threads load + split the A (128 x 16) and Bt (NT x 16) chunks into the canonical no-swizzle K-major UMMA
+//   layout [row/8][k/4][row%8][4] (hi and lo copies); one thread issues 2 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT) and a
 //   tcgen05.commit to the stage's mbarrier; the MMAs run asynchronously while the CTA loads the next chunk into the
 //   other stage (a stage is rewritten only after its commit has arrived).  After the last chunk the accumulator rows
 //   leave TMEM through a shared-memory panel so that global stores are coalesced.
@@ -22,7 +22,7 @@ using namespace pasnl;
 namespace gtc {
 
 constexpr int kM = 128;
-constexpr int kKC = 32;     // k chunk
+constexpr int kKC = 16;     // k chunk per stage: small stages -> 3-4 co-resident CTAs per SM keep ~48 KB of loads in flight
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -108,7 +108,7 @@ __device__ __forceinline__ int tile_off(int row, int kc) { return ((row >> 3) * 
 template <int ROWS, bool VEC4>
 __device__ __forceinline__ void load_tile(float *hi, float *lo, const float *__restrict__ src, long row_base,
                                           long row_limit, long ld, int kb, int k, int warp, int lane) {
-    constexpr int ITEMS = (ROWS / 8) * 2;                // (row group, k half) pairs, 32 float4 each
+    constexpr int ITEMS = (ROWS / 8) * (kKC / 16);       // (row group, 16-wide k slab) pairs, 32 float4 each
     constexpr int PER_WARP = (ITEMS + 7) / 8;
     const int r8 = lane & 7, kq = lane >> 3;
     float4 v[PER_WARP];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
     const uint32_t tmem = tmem_slot;
     constexpr uint32_t idesc = make_idesc(kM, NT);
 
-    // Software pipeline over 32-wide k-chunks with two operand stages: while the tensor core consumes stage s
+    // Software pipeline over 16-wide k-chunks with two operand stages: while the tensor core consumes stage s
     // (asynchronously -- nobody waits for the MMAs of chunk i before loading chunk i+1), all 256 threads load and
     // split the next chunk into stage s^1.  A stage is only rewritten after the commit of the MMAs that read it.
     const int nchunks = (k + kKC - 1) / kKC;
