@@ -105,26 +105,37 @@ __device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int
 constexpr int kSBO = (kKC / 4) * 128;   // bytes
 __device__ __forceinline__ int tile_off(int row, int kc) { return ((row >> 3) * (kKC / 4) + kc) * 32 + (row & 7) * 4; }
 
-template <int ROWS, bool VEC4>
-__device__ __forceinline__ void load_tile(float *hi, float *lo, const float *__restrict__ src, long row_base,
-                                          long row_limit, long ld, int kb, int k, int warp, int lane) {
-    constexpr int ITEMS = (ROWS / 8) * (kKC / 16);       // (row group, 16-wide k slab) pairs, 32 float4 each
-    constexpr int PER_WARP = (ITEMS + 7) / 8;
-    const int r8 = lane & 7, kq = lane >> 3;
+template <int ROWS>
+struct TileRegs {
+    static constexpr int ITEMS = (ROWS / 8) * (kKC / 16);   // (row group, 16-wide k slab) pairs, 32 float4 each
+    static constexpr int PER_WARP = (ITEMS + 7) / 8;
     float4 v[PER_WARP];
+};
+
+// global -> registers (issued one chunk ahead of its use: the loads fly while the previous chunk is split and MMA'd)
+template <int ROWS, bool VEC4>
+__device__ __forceinline__ void tile_fetch(TileRegs<ROWS> &tr, const float *__restrict__ src, long row_base,
+                                           long row_limit, long ld, int kb, int k, int warp, int lane) {
+    const int r8 = lane & 7, kq = lane >> 3;
 #pragma unroll
-    for (int j = 0; j < PER_WARP; ++j) {
+    for (int j = 0; j < TileRegs<ROWS>::PER_WARP; ++j) {
         const int item = warp + 8 * j;
         const int rg = item % (ROWS / 8), h = item / (ROWS / 8);
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (item < ITEMS) v[j] = load4<VEC4>(src, row_base + rg * 8 + r8, row_limit, ld, kb + (kq + 4 * h) * 4, k);
+        tr.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < TileRegs<ROWS>::ITEMS)
+            tr.v[j] = load4<VEC4>(src, row_base + rg * 8 + r8, row_limit, ld, kb + (kq + 4 * h) * 4, k);
     }
+}
+// registers -> split -> shared memory operand tiles.  hi = a & mask, lo = a - hi: one LOP + one FADD per element.
+template <int ROWS>
+__device__ __forceinline__ void tile_store(const TileRegs<ROWS> &tr, float *hi, float *lo, int warp, int lane) {
+    const int r8 = lane & 7, kq = lane >> 3;
 #pragma unroll
-    for (int j = 0; j < PER_WARP; ++j) {
+    for (int j = 0; j < TileRegs<ROWS>::PER_WARP; ++j) {
         const int item = warp + 8 * j;
         const int rg = item % (ROWS / 8), h = item / (ROWS / 8);
-        if (item < ITEMS) {
-            const float4 x = v[j];
+        if (item < TileRegs<ROWS>::ITEMS) {
+            const float4 x = tr.v[j];
             float4 hh, ll;
             hh.x = tf32_hi(x.x); hh.y = tf32_hi(x.y); hh.z = tf32_hi(x.z); hh.w = tf32_hi(x.w);
             ll.x = x.x - hh.x; ll.y = x.y - hh.y; ll.z = x.z - hh.z; ll.w = x.w - hh.w;
@@ -174,7 +185,12 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
     // (asynchronously -- nobody waits for the MMAs of chunk i before loading chunk i+1), all 256 threads load and
     // split the next chunk into stage s^1.  A stage is only rewritten after the commit of the MMAs that read it.
     const int nchunks = (k + kKC - 1) / kKC;
+    const int lane = t & 31;
     uint32_t ph0 = 0, ph1 = 0;
+    TileRegs<kM> ra;
+    TileRegs<NT> rb;
+    tile_fetch<kM, VEC4>(ra, A, row0, rows, lda, 0, k, warp, lane);
+    tile_fetch<NT, VEC4>(rb, Bt, n0, (long)n0 + nvalid, ldb, 0, k, warp, lane);
     for (int i = 0; i < nchunks; ++i) {
         const int sidx = i & 1;
         float *Ahi = smem + sidx * kStage, *Alo = Ahi + kM * kKC;                 // [8][128][4]
@@ -184,9 +200,12 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
             if (sidx == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
             else           { mbar_wait(&bar[1], ph1); ph1 ^= 1u; }
         }
-        // hi = a & mask, lo = a - hi.  The split costs one LOP + one FADD per element (no F2F conversions).
-        load_tile<kM, VEC4>(Ahi, Alo, A, row0, rows, lda, kb, k, warp, t & 31);
-        load_tile<NT, VEC4>(Bhi, Blo, Bt, n0, (long)n0 + nvalid, ldb, kb, k, warp, t & 31);
+        tile_store<kM>(ra, Ahi, Alo, warp, lane);
+        tile_store<NT>(rb, Bhi, Blo, warp, lane);
+        if (i + 1 < nchunks) {      // prefetch the next chunk into registers; consumed in the next iteration
+            tile_fetch<kM, VEC4>(ra, A, row0, rows, lda, kb + kKC, k, warp, lane);
+            tile_fetch<NT, VEC4>(rb, Bt, n0, (long)n0 + nvalid, ldb, kb + kKC, k, warp, lane);
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
