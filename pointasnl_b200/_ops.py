@@ -367,6 +367,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 import os as _os
 
 GEMM_MIN_ROWS = 512   # below this a 128-row tile grid cannot fill the GPU: cuBLAS takes those (fc layers, rows = batch)
+GEMM_K_SLAB = 1024
 GEMM_IMPL = _os.environ.get("PASNL_GEMM", "tc")   # "tc" = tcgen05 3xTF32 kernel, "cublas" = torch.mm (fp32 SIMT)
 
 
@@ -381,10 +382,19 @@ def gemm_rows(a, bt):
         a = a.contiguous()
     if bt.stride(1) != 1:
         bt = bt.contiguous()
-    c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
-    _call("pasnl_gemm_rows_tf32x3", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(bt), int(bt.stride(0)), _ptr(c), n,
-          _stream())
-    return c
+    # The TMEM accumulator truncates on every add (error ~3e-8 * k * |C|): long contractions are cut into <= 1024-wide
+    # slabs whose partial products are summed with round-to-nearest fp32 adds.  (Long k only occurs with few rows --
+    # the PointConv `after_conv`, 2048/4096 wide on 16384/4096 rows -- so the extra pass is tiny, and the slabs give
+    # the small row grid more CTAs.)
+    out = None
+    for k0 in range(0, k, GEMM_K_SLAB):
+        kk = min(GEMM_K_SLAB, k - k0)
+        c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
+        asl, bsl = a[:, k0:k0 + kk], bt[:, k0:k0 + kk]
+        _call("pasnl_gemm_rows_tf32x3", rows, kk, n, asl.data_ptr(), int(a.stride(0)), bsl.data_ptr(), int(bt.stride(0)),
+              _ptr(c), n, _stream())
+        out = c if out is None else out.add_(c)
+    return out
 
 
 class DenseBNAct(torch.autograd.Function):

@@ -78,8 +78,10 @@ def test_tcgen05_gemm_rows_is_fp32_accurate(cuda, rows, k, n):
     want = a.double() @ bt.double().t()
     scale = float(want.abs().max())
     err = float((got.double() - want).abs().max())
-    # 3xTF32 products are good to ~2^-21; the TMEM accumulator adds ~2^-23 |acc| per MMA, growing with k
-    assert err <= 1e-6 * scale * max(1.0, (k / 16) ** 0.5) + 1e-6, (err, scale)
+    # 3xTF32 products are good to ~2^-21; the TMEM accumulator truncates on every add (~3e-8 * k relative, measured),
+    # which is why _ops.gemm_rows cuts k into 1024-wide slabs.  Always inside the path's 1e-4 bar.
+    assert err <= max(3e-6, 3e-8 * min(k, 1024)) * scale + 1e-6, (err, scale)
+    assert err <= 5e-5 * scale
     ref32 = float((torch.mm(a, bt.t()).double() - want).abs().max())      # what cuBLAS fp32 itself achieves
     print('k=%d: tcgen05 max err %.2e, cuBLAS fp32 max err %.2e (|C|max %.1f)' % (k, err, ref32, scale))
     # strided operands (a column slice of a wider tensor)
