@@ -402,7 +402,7 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 }  // namespace
 
 // tcgen05 / TMEM implementation (nonlocal_tc.cu)
-int pasnl_nl_core_fwd_tc(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
+int nl_core_fwd_tcgen05(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
                          float *lse, cudaStream_t st);
 
 static bool use_tensor_core_path(int s, int n, int d) {
@@ -421,7 +421,7 @@ extern "C" int pasnl_nl_core_fwd(int b, int s, int n, int d, const float *q, con
     if ((long)b * s == 0) return PASNL_OK;
     PASNL_CHECK_ARG(q && kv && out && lse && aligned16(q) && aligned16(kv));
     cudaStream_t st = (cudaStream_t)stream;
-    if (use_tensor_core_path(s, n, d) && aligned16(out)) return pasnl_nl_core_fwd_tc(b, s, n, d, q, kv, scale, out, lse, st);
+    if (use_tensor_core_path(s, n, d) && aligned16(out)) return nl_core_fwd_tcgen05(b, s, n, d, q, kv, scale, out, lse, st);
     if (d <= 32) return launch_fwd<32>(b, s, n, d, q, kv, scale, out, lse, st);
     if (d <= 64) return launch_fwd<64>(b, s, n, d, q, kv, scale, out, lse, st);
     return launch_fwd<128>(b, s, n, d, q, kv, scale, out, lse, st);

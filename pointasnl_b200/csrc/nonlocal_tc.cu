@@ -297,7 +297,7 @@ int launch(int b, int s, int n, const float *q, const float *kv, float scale, fl
 }  // namespace tc
 
 // Called by pasnl_nl_core_fwd (nonlocal.cu) for the shapes where a 128 x 64 x D tile fills the tensor pipe.
-int pasnl_nl_core_fwd_tc(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
+int nl_core_fwd_tcgen05(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
                          float *lse, cudaStream_t st) {
     if (d == 32) return tc::launch<32>(b, s, n, q, kv, scale, out, lse, st);
     if (d == 64) return tc::launch<64>(b, s, n, q, kv, scale, out, lse, st);
