@@ -164,6 +164,9 @@ def algorithmic_work(name, a):
     if name == "pasnl_gemm_rows_tf32x3":
         rows, k, n = a[0:3]
         return 4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n, "tensor"
+    if name == "pasnl_gemm_wgrad_tf32x3":
+        rows, m, n = a[0:3]
+        return 4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n, "tensor"
     if name == "pasnl_bn_act_fwd":       # stats read + apply read/write of the (rows, c) activation
         rows, c = a[0:2]
         return 12 * rows * c, 8 * rows * c, "hbm"

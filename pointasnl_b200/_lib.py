@@ -41,6 +41,7 @@ SIGNATURES = {
     "pasnl_nl_core_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pasnl_nl_core_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P]),
     "pasnl_gemm_rows_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P]),
+    "pasnl_gemm_wgrad_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P]),
     "pasnl_bn_workspace_bytes": (c_size_t, [c_int]),
     "pasnl_bn_act_fwd": (c_int, [c_long, c_int, P, P, P, c_float, c_int, P, P, P, P, P, P, c_float, P, P]),
     "pasnl_bn_act_bwd": (c_int, [c_long, c_int, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
@@ -63,7 +64,7 @@ profiler = None    # optional object with before(name, args) / after(name, args)
 KERNELS_PER_CALL = {
     "pasnl_gather_point_grad": 2, "pasnl_gather_rows_grad": 2, "pasnl_group_point_grad": 2,
     "pasnl_three_interpolate_grad": 2, "pasnl_group_concat_grad": 4, "pasnl_nl_core_bwd": 3,
-    "pasnl_bn_act_fwd": 4, "pasnl_bn_act_bwd": 3,
+    "pasnl_bn_act_fwd": 4, "pasnl_bn_act_bwd": 3, "pasnl_gemm_wgrad_tf32x3": 2,
 }
 
 

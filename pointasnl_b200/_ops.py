@@ -361,6 +361,23 @@ class NLCore(torch.autograd.Function):
         return gq, gkv, None
 
 
+def gemm_wgrad(x, dy):
+    """x (rows, m), dy (rows, n) -> x^T dy (m, n): the weight gradient, on tcgen05 (pasnl_gemm_wgrad_tf32x3) for tall
+    problems, cuBLAS otherwise."""
+    rows, m = x.shape
+    n = dy.shape[1]
+    if rows < 4096 or not x.is_cuda or GEMM_IMPL != "tc":
+        return torch.mm(x.t(), dy)
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    if dy.stride(1) != 1:
+        dy = dy.contiguous()
+    dw = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    _call("pasnl_gemm_wgrad_tf32x3", rows, m, n, _ptr(x), int(x.stride(0)), _ptr(dy), int(dy.stride(0)), _ptr(dw), n,
+          _stream())
+    return dw
+
+
 # ------------------------------------------------------------------ dense glue: GEMM + fused BN/activation epilogue
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
@@ -436,6 +453,6 @@ class DenseBNAct(torch.autograd.Function):
         _call("pasnl_bn_act_bwd", rows, cout, _ptr(y), _ptr(dout), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), eps,
               act, _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
         dx = gemm_rows(dy, w2d).reshape(xshape) if ctx.needs_input_grad[0] else None   # dy.W^T: Bt = W as stored
-        dw = torch.mm(x2.t(), dy) if ctx.needs_input_grad[1] else None
+        dw = gemm_wgrad(x2, dy) if ctx.needs_input_grad[1] else None
         dbias = torch.zeros_like(gamma) if ctx.needs_input_grad[2] else None
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None

@@ -293,6 +293,179 @@ int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, l
     return pasnl_launch_status();
 }
 
+// ================================================================ weight-gradient GEMM:  dW[m, n] = sum_r X[r, m] * Y[r, n]
+// Both operands are consumed in their natural row-major layout (the contraction index r is the SLOW one), i.e. as
+// MN-major UMMA operands (instruction descriptor bits 15/16).  Canonical no-swizzle MN-major layout in shared memory:
+//   [r/8][mn/4][r%8][4 floats]  -- core matrix = 8 r-rows x 16 bytes holding 4 consecutive m (or n);
+//   SBO = 128 B (next group of 4 along M/N), LBO = (MN/4)*128 B (next 8 rows of r).
+// One tcgen05.mma.kind::tf32 consumes 8 r-rows.  The row range is split into slabs over CTAs; each CTA accumulates its
+// 128 x NT partial in TMEM and adds it into dW (pre-zeroed) with vector reductions.
+constexpr int kRC = 16;     // r rows per stage
+
+template <int MN>
+struct WTileRegs {
+    static constexpr int ITEMS = (kRC / 8) * (MN / 16);   // (8-row block of r, group of 16 mn) pairs, 32 float4 each
+    static constexpr int PER_WARP = (ITEMS + 7) / 8;
+    float4 v[PER_WARP];
+};
+template <int MN, bool VEC4>
+__device__ __forceinline__ void wtile_fetch(WTileRegs<MN> &tr, const float *__restrict__ src, long r0, long r_end,
+                                            long ld, int c0, int cols, int warp, int lane) {
+    const int r8 = lane & 7, cq = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < WTileRegs<MN>::PER_WARP; ++j) {
+        const int item = warp + 8 * j;
+        const int rb = item % (kRC / 8), cg = item / (kRC / 8);
+        tr.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < WTileRegs<MN>::ITEMS)   // load4(base, row, row_limit, ld, col0, col_limit): 4 consecutive columns
+            tr.v[j] = load4<VEC4>(src, r0 + rb * 8 + r8, r_end, ld, c0 + (cg * 4 + cq) * 4, cols);
+    }
+}
+template <int MN>
+__device__ __forceinline__ void wtile_store(const WTileRegs<MN> &tr, float *hi, float *lo, int warp, int lane) {
+    const int r8 = lane & 7, cq = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < WTileRegs<MN>::PER_WARP; ++j) {
+        const int item = warp + 8 * j;
+        const int rb = item % (kRC / 8), cg = item / (kRC / 8);
+        if (item < WTileRegs<MN>::ITEMS) {
+            const float4 x = tr.v[j];
+            float4 hh, ll;
+            hh.x = tf32_hi(x.x); hh.y = tf32_hi(x.y); hh.z = tf32_hi(x.z); hh.w = tf32_hi(x.w);
+            ll.x = x.x - hh.x; ll.y = x.y - hh.y; ll.z = x.z - hh.z; ll.w = x.w - hh.w;
+            const int o = ((rb * (MN / 4) + cg * 4 + cq) * 8 + r8) * 4;
+            *reinterpret_cast<float4 *>(hi + o) = hh;
+            *reinterpret_cast<float4 *>(lo + o) = ll;
+        }
+    }
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) { return make_idesc(m, n) | (1u << 15) | (1u << 16); }
+
+template <int NT, bool VEC4>
+__global__ void __launch_bounds__(kThreads) gemm_wgrad_kernel(long rows, int m, int n, long slab,
+                                                              const float *__restrict__ X, long ldx,
+                                                              const float *__restrict__ Y, long ldy,
+                                                              float *__restrict__ dW, long ldw) {
+    constexpr int kStage = 2 * kRC * kM + 2 * kRC * NT;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int m0 = blockIdx.y * kM, n0 = blockIdx.z * NT;
+    const long r_begin = (long)blockIdx.x * slab, r_end = min(rows, r_begin + slab);
+    if (r_begin >= r_end) return;
+
+    if (t == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(tmem_cols(NT))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    constexpr uint32_t idesc = make_idesc_mn(kM, NT);
+    constexpr uint32_t lbo_a = (kM / 4) * 128, lbo_b = (NT / 4) * 128;
+
+    const int nchunks = (int)((r_end - r_begin + kRC - 1) / kRC);
+    uint32_t ph0 = 0, ph1 = 0;
+    WTileRegs<kM> ra;
+    WTileRegs<NT> rb;
+    wtile_fetch<kM, VEC4>(ra, X, r_begin, r_end, ldx, m0, m, warp, lane);
+    wtile_fetch<NT, VEC4>(rb, Y, r_begin, r_end, ldy, n0, n, warp, lane);
+    for (int i = 0; i < nchunks; ++i) {
+        const int sidx = i & 1;
+        float *Ahi = smem + sidx * kStage, *Alo = Ahi + kRC * kM;
+        float *Bhi = Alo + kRC * kM, *Blo = Bhi + kRC * NT;
+        if (i >= 2) {
+            if (sidx == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+            else           { mbar_wait(&bar[1], ph1); ph1 ^= 1u; }
+        }
+        wtile_store<kM>(ra, Ahi, Alo, warp, lane);
+        wtile_store<NT>(rb, Bhi, Blo, warp, lane);
+        if (i + 1 < nchunks) {
+            const long rn = r_begin + (long)(i + 1) * kRC;
+            wtile_fetch<kM, VEC4>(ra, X, rn, r_end, ldx, m0, m, warp, lane);
+            wtile_fetch<NT, VEC4>(rb, Y, rn, r_end, ldy, n0, n, warp, lane);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < kRC / 8; ++ks) {
+                const uint64_t ah = make_desc(smem_u32(Ahi) + ks * lbo_a, lbo_a, 128);
+                const uint64_t al = make_desc(smem_u32(Alo) + ks * lbo_a, lbo_a, 128);
+                const uint64_t bh = make_desc(smem_u32(Bhi) + ks * lbo_b, lbo_b, 128);
+                const uint64_t bl = make_desc(smem_u32(Blo) + ks * lbo_b, lbo_b, 128);
+                mma_tf32(tmem, ah, bh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                mma_tf32(tmem, ah, bl, idesc, 1);
+                mma_tf32(tmem, al, bh, idesc, 1);
+            }
+            mma_commit(&bar[sidx]);
+        }
+    }
+    if (((nchunks - 1) & 1) == 0) mbar_wait(&bar[0], ph0);
+    else mbar_wait(&bar[1], ph1);
+    tc_fence_after();
+
+    // ---- epilogue: this CTA's partial (row = m index) is added into dW; warps w and w+4 split the columns
+    const int mrow = m0 + (warp & 3) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    for (int c0 = (warp >> 2) * 32; c0 < NT; c0 += 64) {
+        float v[32];
+        tmem_ld32(tmem + lane_sel + c0, v);
+        if (mrow < m) {
+            float *dst = dW + (long)mrow * ldw + n0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + c0 + i < n) atomicAdd(dst + i, v[i]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols(NT)) : "memory");
+}
+
+template <int NT>
+int launch_wgrad(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW, long ldw,
+                 cudaStream_t st) {
+    const bool vec = (ldx % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(Y) & 15u) == 0);
+    const size_t smem = sizeof(float) * 2 * (size_t)(2 * kRC * kM + 2 * kRC * NT);
+    const int mt = (m + kM - 1) / kM, nt = (n + NT - 1) / NT;
+    // row slabs: enough CTAs for ~3 per SM over all (m, n) tiles, at least 256 rows each
+    long want = (148L * 3 + (long)mt * nt - 1) / ((long)mt * nt);
+    if (want < 1) want = 1;
+    long slab = (rows + want - 1) / want;
+    if (slab < 256) slab = 256;
+    slab = (slab + kRC - 1) / kRC * kRC;
+    const long slabs = (rows + slab - 1) / slab;
+    dim3 grid((unsigned)slabs, (unsigned)mt, (unsigned)nt);
+    cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
+    if (e != cudaSuccess) return (int)e;
+    if (vec) {
+        auto kern = gemm_wgrad_kernel<NT, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, kThreads, smem, st>>>(rows, m, n, slab, X, ldx, Y, ldy, dW, ldw);
+    } else {
+        auto kern = gemm_wgrad_kernel<NT, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, kThreads, smem, st>>>(rows, m, n, slab, X, ldx, Y, ldy, dW, ldw);
+    }
+    return pasnl_launch_status();
+}
+
 }  // namespace gtc
 
 extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb,
@@ -306,4 +479,18 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
     if (n <= 64) return gtc::launch<64>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
     if (n <= 128) return gtc::launch<128>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
     return gtc::launch<256>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
+}
+
+extern "C" int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy,
+                                       float *dW, long ldw, void *stream) {
+    PASNL_CHECK_ARG(rows >= 0 && m >= 1 && n >= 1 && ldx >= m && ldy >= n && ldw >= n);
+    PASNL_CHECK_ARG(dW && (rows == 0 || (X && Y)) && ldw == n && m <= 128 * 65535 && n <= 256 * 65535);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) {
+        cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
+        return (int)e;
+    }
+    if (n <= 32) return gtc::launch_wgrad<32>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
+    if (n <= 64) return gtc::launch_wgrad<64>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
+    return gtc::launch_wgrad<128>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
 }

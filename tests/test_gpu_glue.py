@@ -88,3 +88,20 @@ def test_tcgen05_gemm_rows_is_fp32_accurate(cuda, rows, k, n):
     wide = torch.randn(rows, k + 8, device=cuda)
     got2 = _ops.gemm_rows(wide[:, 4:4 + k], bt)
     torch.testing.assert_close(got2.double(), wide[:, 4:4 + k].double() @ bt.double().t(), rtol=1e-4, atol=1e-4 * scale)
+
+
+@pytest.mark.parametrize("rows,m,n", [(8192, 64, 64), (20000, 128, 128), (16384, 134, 128), (65536, 9, 64), (10000, 3, 32),
+                                      (8192, 259, 256), (4096, 512, 1024), (5000, 70, 48), (16384, 2048, 128)])
+def test_tcgen05_wgrad_gemm(cuda, rows, m, n):
+    """dW = X^T Y through pasnl_gemm_wgrad_tf32x3 (MN-major tcgen05 operands, row slabs + reductions) against fp64."""
+    from pointasnl_b200 import _ops
+    torch.manual_seed(rows + m + n)
+    x = torch.randn(rows, m, device=cuda) + 0.3
+    y = torch.randn(rows, n, device=cuda)
+    got = _ops.gemm_wgrad(x, y)
+    want = x.double().t() @ y.double()
+    scale = float(want.abs().max())
+    err = float((got.double() - want).abs().max())
+    ref32 = float((torch.mm(x.t(), y).double() - want).abs().max())
+    print('rows=%d: tcgen05 wgrad max err %.2e, cuBLAS fp32 %.2e (|dW|max %.1f)' % (rows, err, ref32, scale))
+    assert err <= 5e-5 * scale + 1e-5, (err, scale)
