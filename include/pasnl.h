@@ -175,7 +175,7 @@ int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, co
 
 /* Weight gradient of the same layers (replaces the tf.matmul / conv2d filter gradients TF autodiff emits):
  *     dW[m, n] = sum_r X[r, m] * Y[r, n] ,   X (rows, m), Y (rows, n), dW (m, n) row-major, ldw == n.
- * X = layer input, Y = gradient w.r.t. the GEMM output.  tcgen05, 3xTF32, MN-major operands (no transposes),
+ * X = layer input, Y = gradient w.r.t. the GEMM output.  tcgen05, 3xTF32, operands transposed on the way into shared memory,
  * row slabs reduced into dW (zero-filled here) with fp32 reductions: results are order-dependent at the 1e-7 level. */
 int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
                             long ldw, void *stream);

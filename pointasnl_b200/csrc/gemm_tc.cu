@@ -294,10 +294,9 @@ int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, l
 }
 
 // ================================================================ weight-gradient GEMM:  dW[m, n] = sum_r X[r, m] * Y[r, n]
-// Both operands are consumed in their natural row-major layout (the contraction index r is the SLOW one), i.e. as
-// MN-major UMMA operands (instruction descriptor bits 15/16).  Canonical no-swizzle MN-major layout in shared memory:
-//   [r/8][mn/4][r%8][4 floats]  -- core matrix = 8 r-rows x 16 bytes holding 4 consecutive m (or n);
-//   SBO = 128 B (next group of 4 along M/N), LBO = (MN/4)*128 B (next 8 rows of r).
+// Both operands arrive row-major with the contraction index r as the SLOW one.  (Feeding them as MN-major UMMA operands
+// with SWIZZLE_NONE produced zeros on hardware -- 32-bit MN-major apparently wants the 128B_BASE32B swizzle -- so the
+// tiles are transposed while they are written to shared memory and the proven K-major descriptors are reused.)
 // One tcgen05.mma.kind::tf32 consumes 8 r-rows.  The row range is split into slabs over CTAs; each CTA accumulates its
 // 128 x NT partial in TMEM and adds it into dW (pre-zeroed) with vector reductions.
 constexpr int kRC = 16;     // r rows per stage
@@ -321,6 +320,10 @@ __device__ __forceinline__ void wtile_fetch(WTileRegs<MN> &tr, const float *__re
             tr.v[j] = load4<VEC4>(src, r0 + rb * 8 + r8, r_end, ld, c0 + (cg * 4 + cq) * 4, cols);
     }
 }
+// registers -> split -> TRANSPOSED store: the operand the tensor core sees is K-major with rows = m (or n) and
+// k = r, i.e. element (mn, r) lives at tile_off(mn, r/4) + r%4 (same proven descriptor as the rows GEMM).  A float4 of 4
+// consecutive mn at one r scatters into 4 core-matrix rows (scalar stores, ~4-way bank conflicts: the kernel is
+// latency/HBM bound, not shared-memory bound).
 template <int MN>
 __device__ __forceinline__ void wtile_store(const WTileRegs<MN> &tr, float *hi, float *lo, int warp, int lane) {
     const int r8 = lane & 7, cq = lane >> 3;
@@ -329,17 +332,18 @@ __device__ __forceinline__ void wtile_store(const WTileRegs<MN> &tr, float *hi, 
         const int item = warp + 8 * j;
         const int rb = item % (kRC / 8), cg = item / (kRC / 8);
         if (item < WTileRegs<MN>::ITEMS) {
-            const float4 x = tr.v[j];
-            float4 hh, ll;
-            hh.x = tf32_hi(x.x); hh.y = tf32_hi(x.y); hh.z = tf32_hi(x.z); hh.w = tf32_hi(x.w);
-            ll.x = x.x - hh.x; ll.y = x.y - hh.y; ll.z = x.z - hh.z; ll.w = x.w - hh.w;
-            const int o = ((rb * (MN / 4) + cg * 4 + cq) * 8 + r8) * 4;
-            *reinterpret_cast<float4 *>(hi + o) = hh;
-            *reinterpret_cast<float4 *>(lo + o) = ll;
+            const float xs[4] = {tr.v[j].x, tr.v[j].y, tr.v[j].z, tr.v[j].w};
+            const int r = rb * 8 + r8, mn0 = (cg * 4 + cq) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float hh = tf32_hi(xs[e]);
+                const int o = tile_off(mn0 + e, r >> 2) + (r & 3);
+                hi[o] = hh;
+                lo[o] = xs[e] - hh;
+            }
         }
     }
 }
-__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) { return make_idesc(m, n) | (1u << 15) | (1u << 16); }
 
 template <int NT, bool VEC4>
 __global__ void __launch_bounds__(kThreads) gemm_wgrad_kernel(long rows, int m, int n, long slab,
@@ -370,8 +374,8 @@ __global__ void __launch_bounds__(kThreads) gemm_wgrad_kernel(long rows, int m, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    constexpr uint32_t idesc = make_idesc_mn(kM, NT);
-    constexpr uint32_t lbo_a = (kM / 4) * 128, lbo_b = (NT / 4) * 128;
+    constexpr uint32_t idesc = make_idesc(kM, NT);
+    static_assert(kRC == kKC, "the transposed operand tiles reuse tile_off() of the rows GEMM");
 
     const int nchunks = (int)((r_end - r_begin + kRC - 1) / kRC);
     uint32_t ph0 = 0, ph1 = 0;
@@ -401,10 +405,10 @@ __global__ void __launch_bounds__(kThreads) gemm_wgrad_kernel(long rows, int m, 
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < kRC / 8; ++ks) {
-                const uint64_t ah = make_desc(smem_u32(Ahi) + ks * lbo_a, lbo_a, 128);
-                const uint64_t al = make_desc(smem_u32(Alo) + ks * lbo_a, lbo_a, 128);
-                const uint64_t bh = make_desc(smem_u32(Bhi) + ks * lbo_b, lbo_b, 128);
-                const uint64_t bl = make_desc(smem_u32(Blo) + ks * lbo_b, lbo_b, 128);
+                const uint64_t ah = make_desc(smem_u32(Ahi) + ks * 256, 128, kSBO);
+                const uint64_t al = make_desc(smem_u32(Alo) + ks * 256, 128, kSBO);
+                const uint64_t bh = make_desc(smem_u32(Bhi) + ks * 256, 128, kSBO);
+                const uint64_t bl = make_desc(smem_u32(Blo) + ks * 256, 128, kSBO);
                 mma_tf32(tmem, ah, bh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
                 mma_tf32(tmem, ah, bl, idesc, 1);
                 mma_tf32(tmem, al, bh, idesc, 1);
