@@ -320,27 +320,39 @@ __device__ __forceinline__ void wtile_fetch(WTileRegs<MN> &tr, const float *__re
             tr.v[j] = load4<VEC4>(src, r0 + rb * 8 + r8, r_end, ld, c0 + (cg * 4 + cq) * 4, cols);
     }
 }
-// registers -> split -> TRANSPOSED store: the operand the tensor core sees is K-major with rows = m (or n) and
-// k = r, i.e. element (mn, r) lives at tile_off(mn, r/4) + r%4 (same proven descriptor as the rows GEMM).  A float4 of 4
-// consecutive mn at one r scatters into 4 core-matrix rows (scalar stores, ~4-way bank conflicts: the kernel is
-// latency/HBM bound, not shared-memory bound).
+// registers -> 4x4 transpose across 4 lanes -> split -> store.  The operand the tensor core sees is K-major with
+// rows = m (or n) and k = r: element (mn, r) at tile_off(mn, r/4) + r%4 (same proven descriptors as the rows GEMM).
+// A lane arrives with 4 consecutive mn at ONE r; the 4 lanes that hold r = 4a..4a+3 of the same mn group swap values
+// with two shfl.xor rounds so that each ends up with 4 consecutive r of ONE mn -- exactly one 16-byte core-matrix row,
+// written with a conflict-free STS.128 (a warp covers 4 x 128 contiguous bytes).
 template <int MN>
 __device__ __forceinline__ void wtile_store(const WTileRegs<MN> &tr, float *hi, float *lo, int warp, int lane) {
     const int r8 = lane & 7, cq = lane >> 3;
+    const bool b0 = lane & 1, b1 = lane & 2;
 #pragma unroll
     for (int j = 0; j < WTileRegs<MN>::PER_WARP; ++j) {
         const int item = warp + 8 * j;
         const int rb = item % (kRC / 8), cg = item / (kRC / 8);
+        float v0 = tr.v[j].x, v1 = tr.v[j].y, v2 = tr.v[j].z, v3 = tr.v[j].w;   // [mn0 + e] at r = rb*8 + r8
+        {   // 2x2 blocks on lane bit 0 / element bit 0
+            const float s0 = b0 ? v0 : v1, s1 = b0 ? v2 : v3;
+            const float g0 = __shfl_xor_sync(FULL_MASK, s0, 1), g1 = __shfl_xor_sync(FULL_MASK, s1, 1);
+            if (b0) { v0 = g0; v2 = g1; } else { v1 = g0; v3 = g1; }
+        }
+        {   // 2x2 blocks on lane bit 1 / element bit 1
+            const float s0 = b1 ? v0 : v2, s1 = b1 ? v1 : v3;
+            const float g0 = __shfl_xor_sync(FULL_MASK, s0, 2), g1 = __shfl_xor_sync(FULL_MASK, s1, 2);
+            if (b1) { v0 = g0; v1 = g1; } else { v2 = g0; v3 = g1; }
+        }
+        // now (v0..v3) = element mn0 + (lane&3) at r = rb*8 + 4*((lane>>2)&1) + 0..3
         if (item < WTileRegs<MN>::ITEMS) {
-            const float xs[4] = {tr.v[j].x, tr.v[j].y, tr.v[j].z, tr.v[j].w};
-            const int r = rb * 8 + r8, mn0 = (cg * 4 + cq) * 4;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float hh = tf32_hi(xs[e]);
-                const int o = tile_off(mn0 + e, r >> 2) + (r & 3);
-                hi[o] = hh;
-                lo[o] = xs[e] - hh;
-            }
+            float4 hh, ll;
+            hh.x = tf32_hi(v0); hh.y = tf32_hi(v1); hh.z = tf32_hi(v2); hh.w = tf32_hi(v3);
+            ll.x = v0 - hh.x; ll.y = v1 - hh.y; ll.z = v2 - hh.z; ll.w = v3 - hh.w;
+            const int mn = (cg * 4 + cq) * 4 + (lane & 3);
+            const int o = tile_off(mn, rb * 2 + ((r8 >> 2) & 1));
+            *reinterpret_cast<float4 *>(hi + o) = hh;
+            *reinterpret_cast<float4 *>(lo + o) = ll;
         }
     }
 }
