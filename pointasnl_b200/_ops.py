@@ -366,7 +366,8 @@ def gemm_wgrad(x, dy):
     problems, cuBLAS otherwise."""
     rows, m = x.shape
     n = dy.shape[1]
-    if rows < 4096 or not x.is_cuda or GEMM_IMPL != "tc":
+    # the UMMA tile is 128 wide in m: inputs with a handful of channels (xyz: 3, 6, 9) would be >90 % padding
+    if rows < 4096 or m < 32 or not x.is_cuda or GEMM_IMPL != "tc":
         return torch.mm(x.t(), dy)
     if x.stride(1) != 1:
         x = x.contiguous()

@@ -332,7 +332,7 @@ int apply_grid(long rows, int rpb) {
     return (int)(blocks < 1 ? 1 : blocks);
 }
 int reduce_grid(long rows, int rpb) {
-    long blocks = (rows + (long)rpb * 32 - 1) / ((long)rpb * 32);   // >= 32 rows per thread-row
+    long blocks = (rows + (long)rpb * 8 - 1) / ((long)rpb * 8);     // >= 8 rows per thread-row (2 unrolled trips)
     if (blocks > 148L * 8) blocks = 148L * 8;
     return (int)(blocks < 1 ? 1 : blocks);
 }
