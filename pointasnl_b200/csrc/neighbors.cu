@@ -9,8 +9,8 @@
 // Common shape: a tiled pairwise-distance sweep.  grid = (query tiles, b); the support cloud is streamed through
 // shared memory in tiles of kTile points staged with TMA bulk copies (cp.async.bulk + mbarrier, see common.cuh);
 //   * ball query / k-NN: one WARP per query, lanes sweep 32 support points at a time (stride-3 float reads from
-//     shared memory are bank-conflict free), ballot + popc give the ordered compaction the "first nsample in index
-//     order" / "ascending (d, index)" contracts need;
+//     shared memory are bank-conflict free); ball query: ballot + popc ordered compaction ("first nsample in index
+//     order"); k-NN: warp-select on 64-bit (distance, index) keys (queue + bitonic sort/merge in registers);
 //   * three-NN: one THREAD per query, all lanes read the same support point (shared-memory broadcast).
 // These sweeps are FP32/issue bound for n >~ 4k and latency bound below; compulsory HBM traffic is
 // 12*b*(n+m) + outputs, the support tiles of all query tiles of a cloud are served from L2.
@@ -91,31 +91,62 @@ __global__ void __launch_bounds__(kThreads) ball_query_kernel(int n, int m, floa
 }
 
 // ---------------------------------------------------------------- exact k-NN
-// Warp-distributed sorted list: position p = r*32 + lane holds the p-th nearest so far.
+// Warp-select.  Keys are 64-bit (distance bits << 32 | index): distances are non-negative, so unsigned order on the
+// key IS the (distance, index) lexicographic order the contract asks for -- ties need no special handling.
+// The current k best live in registers as a sorted list spread over the warp (position r*32 + lane, L = R*32 >= k
+// entries, +inf padded).  Candidates below the k-th key are ballot-compacted into a per-warp shared-memory queue;
+// whenever 32 are pending they are bitonic-sorted (15 shuffle stages) and bitonic-merged into the list (log2 L stages):
+// ~200 warp instructions per 32 candidates instead of ~25 per candidate for one-at-a-time insertion.
+constexpr unsigned long long kInfKey = 0x7f800000ffffffffull;   // (+inf, idx max)
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    const unsigned lo = __shfl_xor_sync(FULL_MASK, (unsigned)v, m);
+    const unsigned hi = __shfl_xor_sync(FULL_MASK, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ unsigned long long warp_sort_asc(unsigned long long v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long o = shfl_xor_u64(v, j);
+            const bool up = ((lane & k) == 0);            // ascending block
+            const bool lower = ((lane & j) == 0);
+            const bool take_min = (up == lower);
+            v = take_min ? (v < o ? v : o) : (v > o ? v : o);
+        }
+    }
+    return v;
+}
+// list (sorted ascending over positions r*32+lane) <- k smallest of (list U 32 sorted candidates c, one per lane)
 template <int R>
-__device__ __forceinline__ void knn_insert(float (&bd)[R], int (&bi)[R], float dc, int ic, int lane) {
-    int pos = 0;
+__device__ __forceinline__ void merge_candidates(unsigned long long (&list)[R], unsigned long long c, int lane) {
+    // element-wise min of the list's LAST 32 positions with the candidates reversed: the result is a bitonic
+    // sequence containing the L smallest keys of the union (classic bitonic merge step, candidates padded with +inf)
+    const unsigned long long crev = __shfl_sync(FULL_MASK, (unsigned)c, 31 - lane) |
+                                    ((unsigned long long)__shfl_sync(FULL_MASK, (unsigned)(c >> 32), 31 - lane) << 32);
+    list[R - 1] = list[R - 1] < crev ? list[R - 1] : crev;
+    // bitonic merge network over L = R*32 positions: strides >= 32 pair registers of the same lane, strides < 32 shuffle
 #pragma unroll
-    for (int r = 0; r < R; ++r) pos += __popc(__ballot_sync(FULL_MASK, bd[r] <= dc));
+    for (int st = (R * 32) >> 1; st >= 32; st >>= 1) {
 #pragma unroll
-    for (int r = R - 1; r >= 0; --r) {
-        float ud = __shfl_up_sync(FULL_MASK, bd[r], 1);
-        int ui = __shfl_up_sync(FULL_MASK, bi[r], 1);
-        if (r > 0) {
-            const float cd = __shfl_sync(FULL_MASK, bd[r - 1], 31);
-            const int ci = __shfl_sync(FULL_MASK, bi[r - 1], 31);
-            if (lane == 0) {
-                ud = cd;
-                ui = ci;
+        for (int r = 0; r < R; ++r) {
+            const int pr = r ^ (st >> 5);
+            if (pr > r) {
+                const unsigned long long a = list[r], b2 = list[pr];
+                list[r] = a < b2 ? a : b2;
+                list[pr] = a < b2 ? b2 : a;
             }
         }
-        const int p = r * 32 + lane;
-        if (p == pos) {
-            bd[r] = dc;
-            bi[r] = ic;
-        } else if (p > pos) {
-            bd[r] = ud;
-            bi[r] = ui;
+    }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned long long o = shfl_xor_u64(list[r], j);
+            const bool lower = ((lane & j) == 0);
+            list[r] = lower ? (list[r] < o ? list[r] : o) : (list[r] > o ? list[r] : o);
         }
     }
 }
@@ -124,7 +155,9 @@ template <int R>
 __global__ void __launch_bounds__(kThreads) knn_kernel(int n, int m, int k, const float *__restrict__ xyz1,
                                                        const float *__restrict__ xyz2, int *__restrict__ idx,
                                                        float *__restrict__ dist) {
+    static_assert(R == 1 || R == 2 || R == 4, "list length must be a power of two");
     __shared__ __align__(16) TileStage st;
+    __shared__ unsigned long long queue[kWarps][64];
     constexpr int U = 4;  // 32-point chunks in flight per lane
     const int bi_ = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * kWarps + warp;
@@ -137,21 +170,31 @@ __global__ void __launch_bounds__(kThreads) knn_kernel(int n, int m, int k, cons
         qy = __ldg(qp + 1);
         qz = __ldg(qp + 2);
     }
-    float bd[R];
-    int bi[R];
+    unsigned long long list[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        bd[r] = __int_as_float(0x7f800000);
-        bi[r] = 0;
-    }
-    float tau = __int_as_float(0x7f800000);  // distance at sorted position k-1
-    int nfill = 0;
+    for (int r = 0; r < R; ++r) list[r] = kInfKey;
+    unsigned long long tau = kInfKey;          // key at sorted position k-1: a candidate must be strictly below it
+    int qn = 0;                                // queued candidates (warp-uniform)
     const int rk = (k - 1) >> 5, lk = (k - 1) & 31;
+    unsigned long long *wq = queue[warp];
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (threadIdx.x == 0) {
         mbar_init(&st.bar, 1);
         fence_mbar_init();
     }
     uint32_t parity = 0;
+
+    auto flush = [&](int take) {               // merge the first `take` (<= 32) queued keys into the list
+        unsigned long long c = lane < take ? wq[lane] : kInfKey;
+        c = warp_sort_asc(c, lane);
+        merge_candidates<R>(list, c, lane);
+        unsigned long long t = list[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) t = (r == rk) ? list[r] : t;
+        const unsigned tlo = __shfl_sync(FULL_MASK, (unsigned)t, lk), thi = __shfl_sync(FULL_MASK, (unsigned)(t >> 32), lk);
+        tau = ((unsigned long long)thi << 32) | tlo;
+    };
+
     for (int tile0 = 0; tile0 < n; tile0 += kTile) {
         __syncthreads();
         const int tn = min(kTile, n - tile0);
@@ -160,41 +203,47 @@ __global__ void __launch_bounds__(kThreads) knn_kernel(int n, int m, int k, cons
         parity ^= 1u;
         if (!valid) continue;
         for (int c0 = 0; c0 < tn; c0 += 32 * U) {
-            float d[U];
+            unsigned long long key[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int kk = c0 + u * 32 + lane;
-                d[u] = __int_as_float(0x7fc00000);  // NaN: never a candidate
-                if (kk < tn) d[u] = dist2_nofma(qx - pts[kk * 3 + 0], qy - pts[kk * 3 + 1], qz - pts[kk * 3 + 2]);
+                key[u] = kInfKey;
+                if (kk < tn) {
+                    const float d = dist2_nofma(qx - pts[kk * 3 + 0], qy - pts[kk * 3 + 1], qz - pts[kk * 3 + 2]);
+                    key[u] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(tile0 + kk);
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool in_range = c0 + u * 32 + lane < tn;
-                unsigned bal = __ballot_sync(FULL_MASK, in_range && (d[u] < tau || nfill < k));
-                while (bal) {  // ascending lane == ascending support index: later equal distances go behind
-                    const int src = __ffs(bal) - 1;
-                    bal &= bal - 1;
-                    const float dc = __shfl_sync(FULL_MASK, d[u], src);
-                    if (dc < tau || nfill < k) {
-                        knn_insert<R>(bd, bi, dc, tile0 + c0 + u * 32 + src, lane);
-                        nfill = min(nfill + 1, k);
-                        float t = bd[0];
-#pragma unroll
-                        for (int r = 1; r < R; ++r) t = (r == rk) ? bd[r] : t;
-                        tau = __shfl_sync(FULL_MASK, t, lk);
+                const bool cand = key[u] < tau;
+                const unsigned bal = __ballot_sync(FULL_MASK, cand);
+                if (bal) {
+                    if (cand) wq[qn + __popc(bal & lt_mask)] = key[u];
+                    qn += __popc(bal);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        flush(32);
+                        // slide the (< 32) remaining keys to the front; keys no longer below tau could be dropped,
+                        // keeping them is harmless (they lose in the next merge)
+                        const unsigned long long rest = (lane + 32 < qn) ? wq[lane + 32] : kInfKey;
+                        __syncwarp();
+                        wq[lane] = rest;
+                        qn -= 32;
+                        __syncwarp();
                     }
                 }
             }
         }
     }
     if (valid) {
+        if (qn > 0) flush(qn);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int p = r * 32 + lane;
             if (p < k) {
                 const size_t o = ((size_t)bi_ * m + q) * k + p;
-                idx[o] = bi[r];
-                if (dist) dist[o] = bd[r];
+                idx[o] = (int)(unsigned)list[r];
+                if (dist) dist[o] = __uint_as_float((unsigned)(list[r] >> 32));
             }
         }
     }
@@ -275,12 +324,9 @@ extern "C" int pasnl_knn(int b, int n, int m, int k, const float *xyz1, const fl
     PASNL_CHECK_ARG(xyz1 && xyz2 && idx && b <= 65535);
     dim3 grid((unsigned)ceil_div_i(m, kWarps), (unsigned)b);
     cudaStream_t st = (cudaStream_t)stream;
-    switch ((k + 31) / 32) {
-        case 1: knn_kernel<1><<<grid, kThreads, 0, st>>>(n, m, k, xyz1, xyz2, idx, dist); break;
-        case 2: knn_kernel<2><<<grid, kThreads, 0, st>>>(n, m, k, xyz1, xyz2, idx, dist); break;
-        case 3: knn_kernel<3><<<grid, kThreads, 0, st>>>(n, m, k, xyz1, xyz2, idx, dist); break;
-        default: knn_kernel<4><<<grid, kThreads, 0, st>>>(n, m, k, xyz1, xyz2, idx, dist); break;
-    }
+    if (k <= 32) knn_kernel<1><<<grid, kThreads, 0, st>>>(n, m, k, xyz1, xyz2, idx, dist);
+    else if (k <= 64) knn_kernel<2><<<grid, kThreads, 0, st>>>(n, m, k, xyz1, xyz2, idx, dist);
+    else knn_kernel<4><<<grid, kThreads, 0, st>>>(n, m, k, xyz1, xyz2, idx, dist);
     return pasnl_launch_status();
 }
 
