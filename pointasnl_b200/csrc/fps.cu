@@ -6,8 +6,7 @@
 //   * one CTA (or one thread-block CLUSTER for big clouds) per cloud, persistent over all m rounds;
 //   * the cloud is staged once into shared memory with a TMA bulk copy, then every thread keeps its P points AND
 //     their running min distances in registers for the whole kernel -- nothing touches global memory in the loop;
-//   * per round: register sweep, warp arg-max with one redux.sync on the distance bits (+ a tie-key redux only when
-//     several candidates share the maximum),
+//   * per round: register sweep, warp arg-max with two redux.sync (max of the distance bits, min of the tie key),
 //     one shared-memory hop + ONE __syncthreads, second redux pair computed redundantly by every warp;
 //   * clusters: CTA winners are pushed to every peer's shared memory (DSMEM) and combined after one cluster barrier.
 // FPS is latency/sync bound, not HBM bound (compulsory traffic is 12*b*n + 4*b*m bytes in total).
@@ -65,18 +64,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
         : "memory");
 }
 
-// Arg-max of (bits, then smallest tk) over the warp: returns the winning LANE (same value on every lane) or -1 when no
-// lane holds a candidate (tk == 0xffffffff marks "none").  One redux.sync finds the maximum distance; the tie-key
-// redux is only needed when several candidates share that maximum (duplicates, lattice data) -- a warp-uniform
-// branch, so the common round pays one redux + one ballot.
-__device__ __forceinline__ int warp_argmax_lane(unsigned bits, unsigned tk) {
-    const unsigned wbits = __reduce_max_sync(FULL_MASK, bits);
-    const bool at_max = bits == wbits && tk != 0xffffffffu;
-    const unsigned mask = __ballot_sync(FULL_MASK, at_max);
-    if (mask == 0u) return -1;
-    if (__popc(mask) == 1) return __ffs(mask) - 1;
-    const unsigned wtk = __reduce_min_sync(FULL_MASK, at_max ? tk : 0xffffffffu);
-    return __ffs(__ballot_sync(FULL_MASK, at_max && tk == wtk)) - 1;
+// Reduce (bits, tk) over the warp: returns true on the single winning lane.
+__device__ __forceinline__ bool warp_argmax(unsigned bits, unsigned tk, unsigned &wbits, unsigned &wtk) {
+    wbits = __reduce_max_sync(FULL_MASK, bits);
+    wtk = __reduce_min_sync(FULL_MASK, bits == wbits ? tk : 0xffffffffu);
+    return bits == wbits && tk == wtk && tk != 0xffffffffu;
 }
 
 template <int P, int THREADS, bool CLUSTER>
@@ -151,18 +143,18 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(int n, int m, int chunk, c
             bbits = better ? bits : bbits;
             btk = better ? tk : btk;
         }
-        // ---- warp level: the winning lane writes the whole slot (an empty warp writes a "none" slot)
-        const int wsrc = warp_argmax_lane(bbits, btk);
-        if (lane == max(wsrc, 0)) {
-            Slot sl;
-            sl.bits = wsrc < 0 ? 0u : bbits;
-            sl.tk = wsrc < 0 ? 0xffffffffu : btk;
-            const int kl = wsrc < 0 ? 0 : tie_key_decode(btk) - base;
-            sl.x = pts[kl * 3 + 0];
-            sl.y = pts[kl * 3 + 1];
-            sl.z = pts[kl * 3 + 2];
-            sl.pad[0] = sl.pad[1] = sl.pad[2] = 0u;
-            wslot[pb][warp] = sl;
+        // ---- warp level
+        unsigned wbits, wtk;
+        const bool win = warp_argmax(bbits, btk, wbits, wtk);
+        if (lane == 0) {
+            wslot[pb][warp].bits = wbits;
+            wslot[pb][warp].tk = wtk;
+        }
+        if (win) {
+            const int kl = tie_key_decode(wtk) - base;
+            wslot[pb][warp].x = pts[kl * 3 + 0];
+            wslot[pb][warp].y = pts[kl * 3 + 1];
+            wslot[pb][warp].z = pts[kl * 3 + 2];
         }
         __syncthreads();
         // ---- CTA level: every warp reduces the NW slots redundantly (no second barrier needed)
@@ -171,7 +163,10 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(int n, int m, int chunk, c
             sbits = wslot[pb][lane].bits;
             stk = wslot[pb][lane].tk;
         }
-        const int src = max(warp_argmax_lane(sbits, stk), 0);
+        unsigned cbits, ctk;
+        warp_argmax(sbits, stk, cbits, ctk);
+        int src = __ffs(__ballot_sync(FULL_MASK, lane < NW && sbits == cbits && stk == ctk)) - 1;
+        src = max(src, 0);
 
         if constexpr (CLUSTER) {
             // warp 0 pushes this CTA's winner into cslot[pb][rank] of EVERY CTA of the cluster (itself included)
@@ -180,8 +175,7 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(int n, int m, int chunk, c
             if (warp == 0 && lane < csize) {
                 const uint32_t dst = map_to_rank(&cslot[pb][rank], lane);
                 const uint32_t rbar = map_to_rank(&xbar[pb], lane);
-                st_async_v4(dst, wslot[pb][src].bits, wslot[pb][src].tk, __float_as_uint(wslot[pb][src].x),
-                            __float_as_uint(wslot[pb][src].y), rbar);
+                st_async_v4(dst, cbits, ctk, __float_as_uint(wslot[pb][src].x), __float_as_uint(wslot[pb][src].y), rbar);
                 st_async_v4(dst + 16, __float_as_uint(wslot[pb][src].z), 0u, 0u, 0u, rbar);
             }
             mbar_wait_cluster(&xbar[pb], (xparity >> pb) & 1u);
@@ -191,17 +185,19 @@ __global__ void __launch_bounds__(THREADS) fps_kernel(int n, int m, int chunk, c
                 gbits = cslot[pb][lane].bits;
                 gtk = cslot[pb][lane].tk;
             }
-            const int csrc = max(warp_argmax_lane(gbits, gtk), 0);
+            unsigned fbits, ftk;
+            warp_argmax(gbits, gtk, fbits, ftk);
+            int csrc = __ffs(__ballot_sync(FULL_MASK, lane < csize && gbits == fbits && gtk == ftk)) - 1;
+            csrc = max(csrc, 0);
             x1 = cslot[pb][csrc].x;
             y1 = cslot[pb][csrc].y;
             z1 = cslot[pb][csrc].z;
-            const unsigned ftk = cslot[pb][csrc].tk;
             if (t == 0 && rank == 0) cloud_out[j] = tie_key_decode(ftk);
         } else {
             x1 = wslot[pb][src].x;
             y1 = wslot[pb][src].y;
             z1 = wslot[pb][src].z;
-            if (t == 0) cloud_out[j] = tie_key_decode(wslot[pb][src].tk);
+            if (t == 0) cloud_out[j] = tie_key_decode(ctk);
         }
     }
     if constexpr (CLUSTER) {
@@ -236,19 +232,15 @@ __global__ void __launch_bounds__(1024) fps_generic_kernel(int n, int m, const f
                 bbits = bits; btk = tk; bx = x2; by = y2; bz = z2;
             }
         }
-        const int wsrc = warp_argmax_lane(bbits, btk);
-        if (lane == max(wsrc, 0)) {
-            Slot sl;
-            sl.bits = wsrc < 0 ? 0u : bbits;
-            sl.tk = wsrc < 0 ? 0xffffffffu : btk;
-            sl.x = bx; sl.y = by; sl.z = bz;
-            sl.pad[0] = sl.pad[1] = sl.pad[2] = 0u;
-            wslot[pb][warp] = sl;
-        }
+        unsigned wbits, wtk;
+        const bool win = warp_argmax(bbits, btk, wbits, wtk);
+        if (lane == 0) { wslot[pb][warp].bits = wbits; wslot[pb][warp].tk = wtk; }
+        if (win) { wslot[pb][warp].x = bx; wslot[pb][warp].y = by; wslot[pb][warp].z = bz; }
         __syncthreads();
-        const int src = max(warp_argmax_lane(wslot[pb][lane].bits, wslot[pb][lane].tk), 0);
+        unsigned sbits = wslot[pb][lane].bits, stk = wslot[pb][lane].tk, cbits, ctk;
+        warp_argmax(sbits, stk, cbits, ctk);
+        int src = max(__ffs(__ballot_sync(FULL_MASK, sbits == cbits && stk == ctk)) - 1, 0);
         x1 = wslot[pb][src].x; y1 = wslot[pb][src].y; z1 = wslot[pb][src].z;
-        const unsigned ctk = wslot[pb][src].tk;
         if (t == 0) o[j] = tie_key_decode(ctk);
     }
 }
