@@ -297,6 +297,7 @@ def main():
     points = args.points or (1024 if args.workload == "cls" else 10240)
     workload_name = ("pointasnl_cls" + ("+AS" if args.AS else "") if args.workload == "cls" else "pointasnl_sem_seg_res") \
         + f" B={batch} N={points} per GPU, synthetic"
+    metric = METRIC if args.workload == "cls" else f"point-clouds/sec fwd+bwd pointasnl_sem_seg_res B={batch} N={points}"
     config = {"workload": workload_name, "step": "forward + loss + backward + grad all-reduce + Adam",
               "parallelism": f"dp{world}", "global_batch": batch * world}
 
@@ -308,7 +309,7 @@ def main():
         steps = max(1, min(args.steps, 3))
         warm = 0
         val, ms, cores, kind, sample = run_cpu_reference(args, batch, points, steps, warm)
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                 "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
@@ -437,7 +438,7 @@ def main():
         except Exception as e:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {**config, "l2": "flushed (256 MiB memset) before every timed step, outside the event pair",
