@@ -187,24 +187,29 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
     const int nchunks = (k + kKC - 1) / kKC;
     const int lane = t & 31;
     uint32_t ph0 = 0, ph1 = 0;
-    TileRegs<kM> ra;
-    TileRegs<NT> rb;
-    tile_fetch<kM, VEC4>(ra, A, row0, rows, lda, 0, k, warp, lane);
-    tile_fetch<NT, VEC4>(rb, Bt, n0, (long)n0 + nvalid, ldb, 0, k, warp, lane);
-    for (int i = 0; i < nchunks; ++i) {
+    // register prefetch, distance 2: chunk i+2 is requested while chunk i is split/stored, so two chunks' worth of
+    // global loads per thread are always in flight (the loop is otherwise one memory latency per chunk)
+    TileRegs<kM> ra[2];
+    TileRegs<NT> rb[2];
+    tile_fetch<kM, VEC4>(ra[0], A, row0, rows, lda, 0, k, warp, lane);
+    tile_fetch<NT, VEC4>(rb[0], Bt, n0, (long)n0 + nvalid, ldb, 0, k, warp, lane);
+    if (nchunks > 1) {
+        tile_fetch<kM, VEC4>(ra[1], A, row0, rows, lda, kKC, k, warp, lane);
+        tile_fetch<NT, VEC4>(rb[1], Bt, n0, (long)n0 + nvalid, ldb, kKC, k, warp, lane);
+    }
+    auto step = [&](int i, TileRegs<kM> &rga, TileRegs<NT> &rgb) {
         const int sidx = i & 1;
-        float *Ahi = smem + sidx * kStage, *Alo = Ahi + kM * kKC;                 // [8][128][4]
-        float *Bhi = Alo + kM * kKC, *Blo = Bhi + NT * kKC;                        // [8][NT][4]
-        const int kb = i * kKC;
+        float *Ahi = smem + sidx * kStage, *Alo = Ahi + kM * kKC;
+        float *Bhi = Alo + kM * kKC, *Blo = Bhi + NT * kKC;
         if (i >= 2) {
             if (sidx == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
             else           { mbar_wait(&bar[1], ph1); ph1 ^= 1u; }
         }
-        tile_store<kM>(ra, Ahi, Alo, warp, lane);
-        tile_store<NT>(rb, Bhi, Blo, warp, lane);
-        if (i + 1 < nchunks) {      // prefetch the next chunk into registers; consumed in the next iteration
-            tile_fetch<kM, VEC4>(ra, A, row0, rows, lda, kb + kKC, k, warp, lane);
-            tile_fetch<NT, VEC4>(rb, Bt, n0, (long)n0 + nvalid, ldb, kb + kKC, k, warp, lane);
+        tile_store<kM>(rga, Ahi, Alo, warp, lane);
+        tile_store<NT>(rgb, Bhi, Blo, warp, lane);
+        if (i + 2 < nchunks) {
+            tile_fetch<kM, VEC4>(rga, A, row0, rows, lda, (i + 2) * kKC, k, warp, lane);
+            tile_fetch<NT, VEC4>(rgb, Bt, n0, (long)n0 + nvalid, ldb, (i + 2) * kKC, k, warp, lane);
         }
         fence_async_smem();
         tc_fence_before();
@@ -223,6 +228,10 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
             }
             mma_commit(&bar[sidx]);
         }
+    };
+    for (int i = 0; i < nchunks; i += 2) {
+        step(i, ra[0], rb[0]);
+        if (i + 1 < nchunks) step(i + 1, ra[1], rb[1]);
     }
     // the last commit completes after every earlier MMA of this thread: one wait covers the whole accumulator
     if (((nchunks - 1) & 1) == 0) mbar_wait(&bar[0], ph0);
