@@ -160,7 +160,9 @@ int pasnl_nl_core_bwd(int b, int s, int n, int d, const float *q, const float *k
 size_t pasnl_bn_workspace_bytes(int c);
 int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *gamma, const float *beta, float eps, int act,
                      float *out, float *mean, float *var, const float *bias, float *running_mean, float *running_var,
-                     float decay, void *workspace, void *stream);
+                     float decay, int stats_ready, void *workspace, void *stream);
+/* stats_ready != 0: `workspace` already holds the per-channel sum (c doubles) and sum of squares (c doubles) of y,
+ * accumulated by pasnl_gemm_rows_tf32x3's epilogue (col_stats): the statistics pass over y is skipped. */
 /* Backward of the above: dout (rows, c) -> dy (rows, c) (the gradient w.r.t. the GEMM output), dgamma (c), dbeta (c). */
 int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *dout, const float *gamma, const float *beta,
                      const float *mean, const float *var, float eps, int act, float *dy, float *dgamma, float *dbeta,
@@ -171,7 +173,9 @@ int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *dout, const 
  *     C[rows, n] = A[rows, k] . Bt[n, k]^T ,   A, Bt, C row-major with leading dimensions lda, ldb, ldc (floats).
  * forward: A = x, Bt = W^T;  input gradient: A = dy, Bt = W. */
 int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb, float *C,
-                           long ldc, void *stream);
+                           long ldc, double *col_stats, void *stream);
+/* col_stats: NULL, or 2*n doubles (zeroed by the caller) into which the epilogue adds the per-column sum and sum of
+ * squares of C -- the batch-norm statistics, obtained without another pass over C. */
 
 /* Weight gradient of the same layers (replaces the tf.matmul / conv2d filter gradients TF autodiff emits):
  *     dW[m, n] = sum_r X[r, m] * Y[r, n] ,   X (rows, m), Y (rows, n), dW (m, n) row-major, ldw == n.

@@ -389,13 +389,16 @@ GEMM_K_SLAB = 1024
 GEMM_IMPL = _os.environ.get("PASNL_GEMM", "tc")   # "tc" = tcgen05 3xTF32 kernel, "cublas" = torch.mm (fp32 SIMT)
 
 
-def gemm_rows(a, bt):
+def gemm_rows(a, bt, col_stats=None):
     """a (rows, k) @ bt (n, k)^T -> (rows, n), fp32-accurate, on tcgen05 (pasnl_gemm_rows_tf32x3) when the problem is
-    tall enough, cuBLAS otherwise.  Both operands row-major with a unit inner stride."""
+    tall enough, cuBLAS otherwise.  Both operands row-major with a unit inner stride.
+    col_stats: optional zeroed (2n,) float64 tensor; if the tensor-core path runs as a single k slab its epilogue
+    adds the per-column sum / sum of squares of the result into it and the function returns (c, True)."""
     rows, k = a.shape
     n = bt.shape[0]
     if rows < GEMM_MIN_ROWS or not a.is_cuda or GEMM_IMPL != "tc":
-        return torch.mm(a, bt.t())
+        c = torch.mm(a, bt.t())
+        return c if col_stats is None else (c, False)
     if a.stride(1) != 1:
         a = a.contiguous()
     if bt.stride(1) != 1:
@@ -404,15 +407,16 @@ def gemm_rows(a, bt):
     # slabs whose partial products are summed with round-to-nearest fp32 adds.  (Long k only occurs with few rows --
     # the PointConv `after_conv`, 2048/4096 wide on 16384/4096 rows -- so the extra pass is tiny, and the slabs give
     # the small row grid more CTAs.)
+    fuse_stats = col_stats is not None and k <= GEMM_K_SLAB
     out = None
     for k0 in range(0, k, GEMM_K_SLAB):
         kk = min(GEMM_K_SLAB, k - k0)
         c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
         asl, bsl = a[:, k0:k0 + kk], bt[:, k0:k0 + kk]
         _call("pasnl_gemm_rows_tf32x3", rows, kk, n, asl.data_ptr(), int(a.stride(0)), bsl.data_ptr(), int(bt.stride(0)),
-              _ptr(c), n, _stream())
+              _ptr(c), n, _ptr(col_stats) if fuse_stats else None, _stream())
         out = c if out is None else out.add_(c)
-    return out
+    return out if col_stats is None else (out, fuse_stats)
 
 
 class DenseBNAct(torch.autograd.Function):
@@ -427,14 +431,18 @@ class DenseBNAct(torch.autograd.Function):
         x2 = x.reshape(-1, cin)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        y = gemm_rows(x2, w2d.t().contiguous())          # x.W on tensor cores (3xTF32)
+        ws = torch.zeros((2 * cout,), device=x2.device, dtype=torch.float64)
+        # x.W on tensor cores (3xTF32); the GEMM epilogue also accumulates the batch-norm statistics when it can
+        y, stats_ready = gemm_rows(x2, w2d.t().contiguous(), col_stats=ws)
         rows = y.shape[0]
         out = torch.empty_like(y)
         mean = torch.empty((cout,), device=y.device, dtype=torch.float32)
         var = torch.empty_like(mean)
-        ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
         _call("pasnl_bn_act_fwd", rows, cout, _ptr(y), _ptr(gamma), _ptr(beta), float(eps), int(act), _ptr(out),
-              _ptr(mean), _ptr(var), _ptr(bias), _ptr(running_mean), _ptr(running_var), float(decay), _ptr(ws), _stream())
+              _ptr(mean), _ptr(var), _ptr(bias), _ptr(running_mean), _ptr(running_var), float(decay),
+              1 if stats_ready else 0, _ptr(ws), _stream())
+        if stats_ready:
+            _lib.launch_count -= 2      # no memset / statistics kernels were enqueued by that call
         ctx.save_for_backward(x2, w2d, y, gamma, beta, mean, var)
         ctx.meta = (float(eps), int(act), x.shape)
         return out.reshape(x.shape[:-1] + (cout,))

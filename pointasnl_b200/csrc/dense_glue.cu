@@ -113,14 +113,15 @@ __global__ void bn_stats_kernel(long rows, int c, int cvec, int rpb, const float
 // mean / biased variance from the shifted sums
 __global__ void bn_finalize_kernel(long rows, int c, const float *__restrict__ y, const double *__restrict__ ws,
                                    float *__restrict__ mean, float *__restrict__ var, const float *__restrict__ bias,
-                                   float *__restrict__ running_mean, float *__restrict__ running_var, float decay) {
+                                   float *__restrict__ running_mean, float *__restrict__ running_var, float decay,
+                                   int shifted) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
     const double n = (double)rows;
     const double m = ws[ch] / n;
     double v = ws[c + ch] / n - m * m;
     if (v < 0.0) v = 0.0;
-    const float mu = (float)((double)y[ch] + m);
+    const float mu = (float)((shifted ? (double)y[ch] : 0.0) + m);
     mean[ch] = mu;
     var[ch] = (float)v;
     // moving averages as tf.contrib.layers.batch_norm keeps them (assign_moving_average, biased batch variance)
@@ -343,27 +344,29 @@ extern "C" size_t pasnl_bn_workspace_bytes(int c) { return c > 0 ? sizeof(double
 
 extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *gamma, const float *beta, float eps,
                                 int act, float *out, float *mean, float *var, const float *bias, float *running_mean,
-                                float *running_var, float decay, void *workspace, void *stream) {
+                                float *running_var, float decay, int stats_ready, void *workspace, void *stream) {
     PASNL_CHECK_ARG(rows >= 1 && c >= 1 && act >= 0 && act <= 2 && c <= 4096);
     PASNL_CHECK_ARG(y && gamma && beta && out && mean && var && workspace);
     cudaStream_t st = (cudaStream_t)stream;
     double *ws = (double *)workspace;
-    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st);
-    if (e != cudaSuccess) return (int)e;
+    if (!stats_ready) {
+        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st);
+        if (e != cudaSuccess) return (int)e;
+    }
     const Shape s = make_shape(c, aligned16(y) && aligned16(out));
     PASNL_CHECK_ARG(s.threads <= 1024);
     const size_t smem = sizeof(float) * 2 * (size_t)s.threads * s.vec;
     const int rg = reduce_grid(rows, s.rpb);
     const int ag = apply_grid(rows, s.rpb);
     if (s.vec == 4) {
-        bn_stats_kernel<4><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
+        if (!stats_ready) bn_stats_kernel<4><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
         bn_finalize_kernel<<<ceil_div_i(c, 128), 128, 0, st>>>(rows, c, y, ws, mean, var, bias, running_mean,
-                                                               running_var, decay);
+                                                               running_var, decay, stats_ready ? 0 : 1);
         bn_apply_kernel<4><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, mean, var, gamma, beta, eps, act, out);
     } else {
-        bn_stats_kernel<1><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
+        if (!stats_ready) bn_stats_kernel<1><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
         bn_finalize_kernel<<<ceil_div_i(c, 128), 128, 0, st>>>(rows, c, y, ws, mean, var, bias, running_mean,
-                                                               running_var, decay);
+                                                               running_var, decay, stats_ready ? 0 : 1);
         bn_apply_kernel<1><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, mean, var, gamma, beta, eps, act, out);
     }
     return pasnl_launch_status();

@@ -153,7 +153,8 @@ constexpr int kThreads = 256;   // 8 warps: all load/split; warp w reads TMEM la
 template <int NT, bool VEC4>
 __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, int n, const float *__restrict__ A,
                                                              long lda, const float *__restrict__ Bt, long ldb,
-                                                             float *__restrict__ C, long ldc) {
+                                                             float *__restrict__ C, long ldc,
+                                                             double *__restrict__ stats) {
     constexpr int kStage = 2 * kM * kKC + 2 * NT * kKC;            // floats per operand stage (A hi/lo, B hi/lo)
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t bar[2];                                    // "stage s has been consumed by the tensor core"
@@ -254,6 +255,21 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
                 *reinterpret_cast<float4 *>(stage + lrow * PP + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         __syncthreads();
+        if (stats != nullptr && t < PANEL && n0 + p0 + t < n) {
+            // fused batch-norm statistics: per-column sum and sum of squares of this tile's valid rows, accumulated
+            // around a per-tile shift (row 0) in fp32 and converted to plain sums in fp64 before the atomics
+            const int nv = (int)min((long)kM, rows - row0);
+            const float shift = stage[t];
+            float s1 = 0.f, s2 = 0.f;
+            for (int r = 0; r < nv; ++r) {
+                const float dlt = stage[r * PP + t] - shift;
+                s1 += dlt;
+                s2 = fmaf(dlt, dlt, s2);
+            }
+            const double sh = (double)shift, d1 = (double)s1;
+            atomicAdd(stats + n0 + p0 + t, d1 + nv * sh);
+            atomicAdd(stats + n + n0 + p0 + t, (double)s2 + 2.0 * sh * d1 + nv * sh * sh);
+        }
         constexpr int CPR = PANEL / 4;                            // float4 chunks per row
         for (int e = t; e < kM * CPR; e += kThreads) {
             const int r = e / CPR, c = (e - r * CPR) * 4;
@@ -282,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
 
 template <int NT>
 int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb, float *C, long ldc,
-           cudaStream_t st) {
+           double *stats, cudaStream_t st) {
     const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(Bt) & 15u) == 0);
     const size_t smem = sizeof(float) * 2 * (size_t)(2 * kM * kKC + 2 * NT * kKC);   // two operand stages
@@ -292,12 +308,12 @@ int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, l
         auto kern = gemm_rows_kernel<NT, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
+        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc, stats);
     } else {
         auto kern = gemm_rows_kernel<NT, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc);
+        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc, stats);
     }
     return pasnl_launch_status();
 }
@@ -494,16 +510,16 @@ int launch_wgrad(long rows, int m, int n, const float *X, long ldx, const float 
 }  // namespace gtc
 
 extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb,
-                                      float *C, long ldc, void *stream) {
+                                      float *C, long ldc, double *col_stats, void *stream) {
     PASNL_CHECK_ARG(rows >= 0 && k >= 1 && n >= 1 && lda >= k && ldb >= k && ldc >= n);
     if (rows == 0) return PASNL_OK;
     PASNL_CHECK_ARG(A && Bt && C && rows / 128 < 2147483647L && n <= 256 * 65535);
     cudaStream_t st = (cudaStream_t)stream;
     // UMMA N must be a multiple of 16 (M = 128): the tile is padded in shared memory, stores are bounds-checked
-    if (n <= 32) return gtc::launch<32>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
-    if (n <= 64) return gtc::launch<64>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
-    if (n <= 128) return gtc::launch<128>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
-    return gtc::launch<256>(rows, k, n, A, lda, Bt, ldb, C, ldc, st);
+    if (n <= 32) return gtc::launch<32>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
+    if (n <= 64) return gtc::launch<64>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
+    if (n <= 128) return gtc::launch<128>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
+    return gtc::launch<256>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
 }
 
 extern "C" int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy,
