@@ -93,6 +93,20 @@ int pasnl_group_concat_grad(int b, int n, int c, int m, int nsample, const float
                             int idx_stride, int has_center, float *grad_xyz, float *grad_feat, float *grad_center,
                             void *stream);
 
+/* Max over the neighbour axis: out[g,c] = max_k x[g,k,c] (tf.reduce_max(new_point, axis=[2]), utils/pointasnl_util.py:258;
+ * also the group_all max pooling of utils/pointnet_util.py:125).  x (groups,k,c) -> out (groups,c).  The gradient is
+ * split evenly among tied maxima, as TF's reduce_max gradient does. */
+int pasnl_maxpool_k(long groups, int k, int c, const float *x, float *out, void *stream);
+int pasnl_maxpool_k_grad(long groups, int k, int c, const float *x, const float *out, const float *grad_out,
+                         float *grad_x, void *stream);
+
+/* PointConv-style contraction of the SA / decoding layers (tf.transpose + tf.matmul, utils/pointasnl_util.py:272-273,
+ * 330-333): out[g,ch,w] = sum_t x[g,t,ch] * w[g,t,w].  x (groups,k,c), w (groups,k,32) -> out (groups,c,32).
+ * k % 4 == 0, c % 4 == 0.  Backward: grad_out (groups,c,32) -> grad_x (groups,k,c), grad_w (groups,k,32). */
+int pasnl_pointconv_fwd(int groups, int k, int c, const float *x, const float *w, float *out, void *stream);
+int pasnl_pointconv_bwd(int groups, int k, int c, const float *x, const float *w, const float *grad_out, float *grad_x,
+                        float *grad_w, void *stream);
+
 /* ---------------------------------------------------------------- interpolation (tf_ops/3d_interpolation) */
 
 /* three_nn.  Replaces threenn_cpu(b,n,m,xyz1,xyz2,dist,idx) (tf_interpolate.cpp:60-103).

@@ -213,6 +213,60 @@ class GroupConcat(torch.autograd.Function):
         return g_xyz, g_feat, None, g_center
 
 
+class PointConvContract(torch.autograd.Function):
+    """x (..., k, c), w (..., k, 32) -> x^T w per neighbourhood, (..., c, 32)  (pointasnl_util.py:272-273)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = _f32(x, "x"), _f32(w, "w")
+        k, c = x.shape[-2], x.shape[-1]
+        _require(w.shape[-1] == 32 and w.shape[:-1] == x.shape[:-1], "weight must be (..., k, 32) matching x (..., k, c)")
+        groups = x.numel() // (k * c)
+        out = torch.empty(x.shape[:-2] + (c, 32), device=x.device, dtype=torch.float32)
+        _call("pasnl_pointconv_fwd", groups, k, c, _ptr(x), _ptr(w), _ptr(out), _stream())
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = _f32(g, "grad_out")
+        k, c = x.shape[-2], x.shape[-1]
+        gx, gw = torch.empty_like(x), torch.empty_like(w)
+        _call("pasnl_pointconv_bwd", x.numel() // (k * c), k, c, _ptr(x), _ptr(w), _ptr(g), _ptr(gx), _ptr(gw), _stream())
+        return gx, gw
+
+
+def pointconv_contract(x, w):
+    k, c = x.shape[-2], x.shape[-1]
+    if x.is_cuda and w.shape[-1] == 32 and k % 4 == 0 and c % 4 == 0 and k <= 256 and (k * c + k * 32 + c * 33) * 4 <= 200 * 1024:
+        return PointConvContract.apply(x, w)
+    return torch.matmul(x.transpose(-1, -2), w)
+
+
+class MaxPoolK(torch.autograd.Function):
+    """x (..., k, c) -> max over the k axis (..., c); gradient split evenly among tied maxima (tf.reduce_max)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x, "x")
+        k, c = x.shape[-2], x.shape[-1]
+        groups = x.numel() // (k * c)
+        out = torch.empty(x.shape[:-2] + (c,), device=x.device, dtype=torch.float32)
+        _call("pasnl_maxpool_k", groups, k, c, _ptr(x), _ptr(out), _stream())
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out = ctx.saved_tensors
+        g = _f32(g, "grad_out")
+        k, c = x.shape[-2], x.shape[-1]
+        gx = torch.empty_like(x)
+        _call("pasnl_maxpool_k_grad", x.numel() // (k * c), k, c, _ptr(x), _ptr(out), _ptr(g), _ptr(gx), _stream())
+        return gx
+
+
 # ------------------------------------------------------------------ interpolation
 def three_nn(xyz1, xyz2):
     xyz1, xyz2 = _f32(xyz1, "xyz1"), _f32(xyz2, "xyz2")

@@ -30,7 +30,8 @@ class TrainStep:
         with torch.no_grad():   # materialise every variable (TF would do this at graph-construction time)
             self._forward()
         self.bucket = FlatGradBucket(self.store.parameters())
-        self.opt = torch.optim.Adam(self.bucket.params, lr=lr, capturable=use_graph)
+        # fused=True: one multi-tensor kernel per step (the foreach implementation is ~60 small kernels, 0.95 ms)
+        self.opt = torch.optim.Adam(self.bucket.params, lr=lr, capturable=use_graph, fused=True)
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None

@@ -187,6 +187,38 @@ int warp_grid(long rows, int rows_per_warp) {
     return (int)(blocks < 1 ? 1 : blocks);
 }
 
+// ---------------------------------------------------------------- max over the neighbour axis
+// out[g, c] = max_k x[g, k, c]  (tf.reduce_max(new_point, axis=[2]), utils/pointasnl_util.py:258) and its gradient, which
+// TF splits evenly among tied maxima (indicators / num_selected).  One thread per (group, channel): consecutive threads
+// read consecutive channels, so every k-row is a coalesced access.  HBM bound: 4*G*K*C bytes forward, 8*G*K*C backward.
+__global__ void __launch_bounds__(kThreads) maxpool_k_kernel(long gc, int k, int c, const float *__restrict__ x,
+                                                             float *__restrict__ out) {
+    for (long e = (long)blockIdx.x * kThreads + threadIdx.x; e < gc; e += (long)gridDim.x * kThreads) {
+        const long g = e / c;
+        const int ch = (int)(e - g * c);
+        const float *p = x + g * (long)k * c + ch;
+        float m = __ldg(p);
+        for (int t = 1; t < k; ++t) m = fmaxf(m, __ldg(p + (long)t * c));
+        out[e] = m;
+    }
+}
+__global__ void __launch_bounds__(kThreads) maxpool_k_grad_kernel(long gc, int k, int c, const float *__restrict__ x,
+                                                                  const float *__restrict__ out,
+                                                                  const float *__restrict__ grad_out,
+                                                                  float *__restrict__ grad_x) {
+    for (long e = (long)blockIdx.x * kThreads + threadIdx.x; e < gc; e += (long)gridDim.x * kThreads) {
+        const long g = e / c;
+        const int ch = (int)(e - g * c);
+        const float *p = x + g * (long)k * c + ch;
+        float *q = grad_x + g * (long)k * c + ch;
+        const float m = __ldg(out + e);
+        int cnt = 0;
+        for (int t = 0; t < k; ++t) cnt += (__ldg(p + (long)t * c) == m) ? 1 : 0;
+        const float share = __ldg(grad_out + e) / (float)cnt;
+        for (int t = 0; t < k; ++t) q[(long)t * c] = (__ldg(p + (long)t * c) == m) ? share : 0.f;
+    }
+}
+
 // ---------------------------------------------------------------- three_interpolate
 // out[row, :] = (p1*w1 + p2*w2) + p3*w3 with separate roundings (the x86 reference has no FMA): bit-exact.
 template <int VEC>
@@ -393,5 +425,23 @@ extern "C" int pasnl_three_interpolate_grad(int b, int n, int c, int m, const fl
         three_interp_grad_kernel<1>
             <<<grid_for(rows * c), kThreads, 0, st>>>(rows, n, m, c, grad_out, idx, weight, grad_points);
     }
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_maxpool_k(long groups, int k, int c, const float *x, float *out, void *stream) {
+    PASNL_CHECK_ARG(groups >= 0 && k >= 1 && c >= 1);
+    if (groups == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(x && out);
+    maxpool_k_kernel<<<grid_for(groups * c), kThreads, 0, (cudaStream_t)stream>>>(groups * c, k, c, x, out);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_maxpool_k_grad(long groups, int k, int c, const float *x, const float *out, const float *grad_out,
+                                    float *grad_x, void *stream) {
+    PASNL_CHECK_ARG(groups >= 0 && k >= 1 && c >= 1);
+    if (groups == 0) return PASNL_OK;
+    PASNL_CHECK_ARG(x && out && grad_out && grad_x);
+    maxpool_k_grad_kernel<<<grid_for(groups * c), kThreads, 0, (cudaStream_t)stream>>>(groups * c, k, c, x, out,
+                                                                                        grad_out, grad_x);
     return pasnl_launch_status();
 }

@@ -220,7 +220,7 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
                                                    [max(32, num_channel // 2), nl_channel], is_training, bn_decay,
                                                    weight_decay, scope, bn)
         # skip connection (reference :258-262)
-        skip_spatial = new_point.amax(dim=2)
+        skip_spatial = _ops.MaxPoolK.apply(new_point)                      # max over the K neighbours, fused fwd/bwd
         skip_spatial = tf_util.conv1d(skip_spatial, mlp[-1], 1, padding="VALID", stride=1, bn=bn,
                                       is_training=is_training, scope="skip", bn_decay=bn_decay,
                                       weight_decay=weight_decay)
@@ -232,7 +232,7 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
                                            weight_decay=weight_decay)
         weight = weight_net_hidden(grouped_xyz, [32], scope="weight_net", is_training=is_training, bn_decay=bn_decay,
                                    weight_decay=weight_decay)
-        new_point = torch.matmul(new_point.transpose(2, 3), weight)        # (B, S, C', K) x (B, S, K, 32)
+        new_point = _ops.pointconv_contract(new_point, weight)             # per group (C' x K)(K x 32), one kernel
         new_point = tf_util.conv2d(new_point, mlp[-1], [1, new_point.shape[2]], padding="VALID", stride=[1, 1],
                                    bn=bn, is_training=is_training, scope="after_conv", bn_decay=bn_decay,
                                    weight_decay=weight_decay)
@@ -267,7 +267,7 @@ def PointASNLDecodingLayer(xyz1, xyz2, points1, points2, nsample, mlp, is_traini
         grouped_xyz = grouped_xyz - xyz1.unsqueeze(2)
         weight = weight_net_hidden(grouped_xyz, [32], scope="decode_weight_net", is_training=is_training,
                                    bn_decay=bn_decay, weight_decay=weight_decay)
-        new_points = torch.matmul(grouped_feature.transpose(2, 3), weight)
+        new_points = _ops.pointconv_contract(grouped_feature, weight)
         new_points = tf_util.conv2d(new_points, mlp[0], [1, new_points.shape[2]], padding="VALID", stride=[1, 1],
                                     bn=bn, is_training=is_training, scope="decode_after_conv", bn_decay=bn_decay,
                                     weight_decay=weight_decay)

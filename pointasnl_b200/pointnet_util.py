@@ -34,7 +34,8 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
         for i, num_out_channel in enumerate(mlp):
             new_points = tf_util.conv2d(new_points, num_out_channel, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
                                         is_training=is_training, scope="conv%d" % i, bn_decay=bn_decay)
-        new_points = new_points.amax(dim=2, keepdim=True)
+        from . import _ops
+        new_points = (_ops.MaxPoolK.apply(new_points) if new_points.is_cuda else new_points.amax(dim=2)).unsqueeze(2)
         if mlp2 is not None:
             for i, num_out_channel in enumerate(mlp2):
                 new_points = tf_util.conv2d(new_points, num_out_channel, [1, 1], padding="VALID", stride=[1, 1],

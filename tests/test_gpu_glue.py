@@ -105,3 +105,39 @@ def test_tcgen05_wgrad_gemm(cuda, rows, m, n):
     ref32 = float((torch.mm(x.t(), y).double() - want).abs().max())
     print('rows=%d: tcgen05 wgrad max err %.2e, cuBLAS fp32 %.2e (|dW|max %.1f)' % (rows, err, ref32, scale))
     assert err <= 5e-5 * scale + 1e-5, (err, scale)
+
+
+@pytest.mark.parametrize("shape", [(4, 128, 64, 134), (8, 512, 32, 9), (2, 1, 512, 131), (3, 7, 1, 5)])
+def test_maxpool_over_neighbours_forward_backward_with_ties(cuda, shape):
+    from pointasnl_b200 import _ops
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape)
+    x[..., 0, :] = x[..., -1, :]                          # duplicated neighbours: exact ties wherever they are the max
+    x = torch.round(x * 4) / 4                            # and plenty more ties
+    xd = x.double().requires_grad_(True)
+    want = xd.amax(dim=-2)                                # torch splits the gradient evenly among ties, like TF
+    xc = x.to(cuda).requires_grad_(True)
+    got = _ops.MaxPoolK.apply(xc)
+    assert torch.equal(got.detach().cpu().double(), want.detach())
+    g = torch.randn(want.shape)
+    want.backward(g.double())
+    got.backward(g.to(cuda))
+    torch.testing.assert_close(xc.grad.cpu().double(), xd.grad, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(4, 128, 64, 128), (8, 512, 32, 64), (2, 40, 32, 512), (1, 3, 16, 36), (2, 10, 32, 20)])
+def test_pointconv_contraction_forward_backward(cuda, shape):
+    from pointasnl_b200 import _ops
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape)
+    w = torch.randn(*shape[:-1], 32)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    want = torch.matmul(xd.transpose(-1, -2), wd)
+    xc, wc = x.to(cuda).requires_grad_(True), w.to(cuda).requires_grad_(True)
+    got = _ops.pointconv_contract(xc, wc)
+    torch.testing.assert_close(got.detach().cpu().double(), want.detach(), rtol=1e-4, atol=1e-5)
+    g = torch.randn(want.shape)
+    want.backward(g.double())
+    got.backward(g.to(cuda))
+    torch.testing.assert_close(xc.grad.cpu().double(), xd.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(wc.grad.cpu().double(), wd.grad, rtol=1e-4, atol=1e-5)
