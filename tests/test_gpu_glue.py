@@ -139,5 +139,6 @@ def test_pointconv_contraction_forward_backward(cuda, shape):
     g = torch.randn(want.shape)
     want.backward(g.double())
     got.backward(g.to(cuda))
-    torch.testing.assert_close(xc.grad.cpu().double(), xd.grad, rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(wc.grad.cpu().double(), wd.grad, rtol=1e-4, atol=1e-5)
+    # fp32 dot products of k / 32 / c terms with O(1) inputs: the absolute floor scales with sqrt(#terms)
+    torch.testing.assert_close(xc.grad.cpu().double(), xd.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(wc.grad.cpu().double(), wd.grad, rtol=1e-4, atol=2e-4)
