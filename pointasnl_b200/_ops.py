@@ -421,7 +421,7 @@ def gemm_wgrad(x, dy):
     rows, m = x.shape
     n = dy.shape[1]
     # the UMMA tile is 128 wide in m: inputs with a handful of channels (xyz: 3, 6, 9) would be >90 % padding
-    if rows < 4096 or m < 32 or not x.is_cuda or GEMM_IMPL != "tc":
+    if rows < 4096 or m < 32 or (rows < 16384 and m >= 512) or not x.is_cuda or GEMM_IMPL != "tc":
         return torch.mm(x.t(), dy)
     if x.stride(1) != 1:
         x = x.contiguous()
@@ -450,7 +450,10 @@ def gemm_rows(a, bt, col_stats=None):
     adds the per-column sum / sum of squares of the result into it and the function returns (c, True)."""
     rows, k = a.shape
     n = bt.shape[0]
-    if rows < GEMM_MIN_ROWS or not a.is_cuda or GEMM_IMPL != "tc":
+    # measured on B200 (tools/sweep_gemm2.py): the tcgen05 kernel wins whenever there are >= 128 row tiles; with only
+    # 32 row tiles (rows = 4096: the classifier heads) it needs a wide n to fill the GPU, otherwise cuBLAS' split-k wins
+    use_tc = a.is_cuda and GEMM_IMPL == "tc" and rows >= GEMM_MIN_ROWS and (rows >= 16384 or (n >= 512 and k <= 1024))
+    if not use_tc:
         c = torch.mm(a, bt.t())
         return c if col_stats is None else (c, False)
     if a.stride(1) != 1:
