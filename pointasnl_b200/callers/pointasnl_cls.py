@@ -58,8 +58,7 @@ def get_model(point_cloud, is_training, use_normal=False, bn_decay=None, weight_
 
 def l2_on_weights(store):
     """sum of tf.nn.l2_loss(v) = sum(v^2)/2 over every variable whose name contains 'weights' (:58)."""
-    terms = [0.5 * (v ** 2).sum() for name, v in store.variables().items() if "weights" in name]
-    return torch.stack(terms).sum()
+    return tf_util.l2_loss_sum([v for name, v in store.variables().items() if "weights" in name])
 
 
 def get_loss(pred, label, end_points, uniform_weight=0, weights_decay=1e-4):

@@ -48,9 +48,10 @@ class TrainStep:
             return pointasnl_sem_seg_res.get_loss(pred, self.labels, end_points, self.smpw)
 
     def _fwd_bwd(self):
-        self.bucket.zero()
+        self.bucket.detach()
         loss = self._forward()
         loss.backward()
+        self.bucket.pack()
         self.loss.copy_(loss.detach())
 
     def _eager_step(self):

@@ -24,11 +24,33 @@ class FlatGradBucket:
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("all parameters must be float32 on one device")
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        self.views = list(torch.split(self.flat, [p.numel() for p in self.params]))
+        self.views = [v.view_as(p) for v, p in zip(self.views, self.params)]
+        self.alias()
+
+    def alias(self):
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def zero(self):
         self.flat.zero_()
+
+    def detach(self):
+        """Drop ``p.grad`` before backward so autograd ASSIGNS each gradient instead of accumulating into the bucket
+        (accumulation is one zero-fill plus one add kernel per parameter per step); follow with ``pack()``."""
+        for p in self.params:
+            p.grad = None
+
+    def pack(self):
+        """Copy the freshly produced gradients into the bucket with one multi-tensor copy and re-alias ``p.grad``."""
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v, p in zip(self.views, self.params):
+            if p.grad is None:
+                v.zero_()     # parameter not reached by this step's loss
+        self.alias()
 
     def check_aliasing(self):
         """autograd must have accumulated in place (it does when .grad is pre-populated); guard against a silent

@@ -50,7 +50,7 @@ def test_fused_dense_bn_act_forward_backward(cuda, shape, cout, act):
 def test_tf_util_layers_take_the_fused_path_and_match_op_by_op(cuda):
     from pointasnl_b200 import _lib, tf_util
     torch.manual_seed(0)
-    x = torch.randn(4, 64, 16, 20, device=cuda)
+    x = torch.randn(16, 64, 16, 20, device=cuda)       # 16384 rows: the size class _ops.gemm_rows sends to tcgen05
     store = tf_util.VariableStore(cuda, seed=5)
     with store.as_default():
         c0 = _lib.launch_count

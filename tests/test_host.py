@@ -95,6 +95,13 @@ def _dp_worker(rank, world, port, out):
     bucket.zero()
     ((model(x_all[lo:hi]) - y_all[lo:hi]) ** 2).mean().backward()
     bucket.check_aliasing()
+    accumulated = bucket.flat.clone()
+    # the path TrainStep takes: autograd assigns fresh gradients, one multi-tensor copy packs them into the bucket
+    bucket.detach()
+    ((model(x_all[lo:hi]) - y_all[lo:hi]) ** 2).mean().backward()
+    bucket.pack()
+    bucket.check_aliasing()
+    assert torch.equal(bucket.flat, accumulated)
     bucket.all_reduce_mean()
     slowest = dp.max_over_ranks(float(rank + 1), torch.device("cpu"))
     if rank == 0:
