@@ -15,6 +15,8 @@
 //   tcgen05.commit to the stage's mbarrier; the MMAs run asynchronously while the CTA loads the next chunk into the
 //   other stage (a stage is rewritten only after its commit has arrived).  After the last chunk the accumulator rows
 //   leave TMEM through a shared-memory panel so that global stores are coalesced.
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace pasnl;
@@ -146,7 +148,11 @@ __device__ __forceinline__ void tile_store(const TileRegs<ROWS> &tr, float *hi, 
     }
 }
 
-constexpr int tmem_cols(int nt) { return nt < 32 ? 32 : nt; }   // power of two >= 32 (NT is 32/64/128/256)
+constexpr int tmem_cols(int nt) {   // TMEM allocations are powers of two >= 32 columns
+    int c = 32;
+    while (c < nt) c *= 2;
+    return c;
+}
 
 constexpr int kThreads = 256;   // 8 warps: all load/split; warp w reads TMEM lanes 32*(w%4).. in the epilogue
 
@@ -316,6 +322,353 @@ int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, l
         kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc, stats);
     }
     return pasnl_launch_status();
+}
+
+// ================================================================ persistent, warp-specialised rows GEMM (weights resident)
+// For the layers that dominate a step (rows = B*S*K ~ 10^5..10^6, k <= 144, n <= 128) the weight matrix is tiny: its
+// hi/lo operand tiles (<= 147 KB) are built ONCE per CTA and stay in shared memory while the CTA walks over row tiles.
+// One CTA per SM, 13 warps:
+//   warps 5..12  producers: stream A (128 x 16 chunks) global -> registers (6 chunks in flight per thread) -> split ->
+//                 operand stage ring in shared memory, arrive on full[s]
+//   warp  4      MMA issuer: waits full[s], issues 6 tcgen05.mma (2 k-steps x hi.hi, hi.lo, lo.hi) per chunk into one
+//                 of TWO accumulators in TMEM, tcgen05.commit -> empty[s]; after the tile's last chunk commit -> tfull[b]
+//   warps 0..3   epilogue: wait tfull[b], tcgen05.ld their 32 accumulator rows, release the accumulator (tempty[b]) and
+//                 write C through a private 32x32 shared-memory panel (coalesced 128-byte rows), folding the batch-norm
+//                 column statistics into per-lane fp64 registers that reach global memory once per CTA.
+// The tile loop of the three roles only meets through mbarriers, so loads, tensor-core work and stores of neighbouring
+// tiles overlap; the one-tile-per-CTA kernel above pays load latency, MMA latency and the store drain in sequence.
+constexpr int kPThreads = 13 * 32;
+constexpr int kPProducerWarps = 8;
+constexpr int kPrefetch = 6;       // A chunks in flight per producer thread (6 x 8 KB per CTA ~ HBM latency x 26 B/clk)
+constexpr int kMaxStages = 8;
+constexpr int kPanelPitch = 36;    // floats: 32 columns + 4 (conflict-free 16-byte row writes)
+
+__device__ __forceinline__ int btile_off(int row, int kc, int kq4) { return ((row >> 3) * kq4 + kc) * 32 + (row & 7) * 4; }
+
+template <int NT>
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_rows_persist_kernel(long rows, int k, int kpad, int n, int n0, int nvalid, long ntiles, int nstages,
+                         const float *__restrict__ A, long lda, const float *__restrict__ Bt, long ldb,
+                         float *__restrict__ C, long ldc, double *__restrict__ stats, int vec4) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int kq4 = kpad >> 2;                                   // 16-byte k groups per operand row
+    float *Bhi = smem, *Blo = Bhi + NT * kpad;
+    float *stages = Blo + NT * kpad;                             // nstages x [A hi 128x16 | A lo 128x16]
+    float *panels = stages + (size_t)nstages * (2 * kM * kKC);   // 4 x 32 x kPanelPitch
+
+    if (t == 0) {
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], kPProducerWarps); mbar_init(&empty[s], 1); }
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(tmem_cols(2 * NT))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // resident weights: Bt rows n0..n0+nvalid, k zero-padded to kpad, split once
+        const int r8 = lane & 7, kq = lane >> 3;
+        const int items = (NT / 8) * (kpad / 16);
+        for (int item = warp; item < items; item += kPThreads / 32) {
+            const int rg = item % (NT / 8), h = item / (NT / 8);
+            const int row = rg * 8 + r8, kc = kq + 4 * h;
+            const float4 x = vec4 ? load4<true>(Bt, (long)n0 + row, (long)n0 + nvalid, ldb, kc * 4, k)
+                                  : load4<false>(Bt, (long)n0 + row, (long)n0 + nvalid, ldb, kc * 4, k);
+            float4 hh, ll;
+            hh.x = tf32_hi(x.x); hh.y = tf32_hi(x.y); hh.z = tf32_hi(x.z); hh.w = tf32_hi(x.w);
+            ll.x = x.x - hh.x; ll.y = x.y - hh.y; ll.z = x.z - hh.z; ll.w = x.w - hh.w;
+            const int o = btile_off(row, kc, kq4);
+            *reinterpret_cast<float4 *>(Bhi + o) = hh;
+            *reinterpret_cast<float4 *>(Blo + o) = ll;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int nchunks = kpad / kKC;
+    const long my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+    if (warp >= 5) {
+        // ------------------------------------------------------------------ producers
+        // A warp's instruction stream is serial (~5 cycles per dependent instruction), so the per-chunk path is kept
+        // to a few dozen instructions: every thread owns the same two (row, 16-byte k group) positions of each tile
+        // and walks two pointers; index arithmetic and bounds checks only run on the ragged last tile / last chunk.
+        const int pw = warp - 5;
+        const int r8 = lane & 7, kq = lane >> 3;
+        const int ra = pw * 8 + r8, rb = ra + 64;                 // this thread's two rows inside a tile
+        const int oa = tile_off(ra, kq), ob = tile_off(rb, kq);   // and their float offsets inside an operand stage
+        const int kfull = k / kKC;                                // chunks that need no k bounds check
+        const long tstride = (long)gridDim.x * kM;
+        long frow0 = (long)blockIdx.x * kM;                       // fetch cursor: tile row base, chunk, pointers
+        int fc = 0;
+        const float *pa = A + (frow0 + ra) * lda + kq * 4;
+        const long hop = 64 * lda;
+        bool tfullrows = frow0 + kM <= rows;
+        long remaining_fetch = my_tiles * nchunks;
+        float4 r[kPrefetch][2];
+        auto fetch = [&](float4 (&dst)[2]) {
+            if (vec4 && tfullrows && fc < kfull) {
+                dst[0] = __ldg(reinterpret_cast<const float4 *>(pa));
+                dst[1] = __ldg(reinterpret_cast<const float4 *>(pa + hop));
+            } else if (vec4) {
+                dst[0] = load4<true>(A, frow0 + ra, rows, lda, fc * kKC + kq * 4, k);
+                dst[1] = load4<true>(A, frow0 + rb, rows, lda, fc * kKC + kq * 4, k);
+            } else {
+                dst[0] = load4<false>(A, frow0 + ra, rows, lda, fc * kKC + kq * 4, k);
+                dst[1] = load4<false>(A, frow0 + rb, rows, lda, fc * kKC + kq * 4, k);
+            }
+            pa += kKC;
+            if (++fc == nchunks) {
+                fc = 0;
+                frow0 += tstride;
+                pa = A + (frow0 + ra) * lda + kq * 4;
+                tfullrows = frow0 + kM <= rows;
+            }
+            --remaining_fetch;
+        };
+        auto split_store = [&](const float4 &x, float *hi, float *lo) {
+            float4 hh, ll;
+            hh.x = tf32_hi(x.x); hh.y = tf32_hi(x.y); hh.z = tf32_hi(x.z); hh.w = tf32_hi(x.w);
+            ll.x = x.x - hh.x; ll.y = x.y - hh.y; ll.z = x.z - hh.z; ll.w = x.w - hh.w;
+            *reinterpret_cast<float4 *>(hi) = hh;
+            *reinterpret_cast<float4 *>(lo) = ll;
+        };
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u)
+            if (remaining_fetch > 0) fetch(r[u]);
+        int s = 0;
+        uint32_t par = 1;                                         // empty[] starts "already released"
+        float *stage = stages;
+        for (long left = my_tiles * nchunks; left > 0; left -= kPrefetch) {
+#pragma unroll
+            for (int u = 0; u < kPrefetch; ++u) {
+                if (u < left) {
+                    mbar_wait(&empty[s], par);
+                    split_store(r[u][0], stage + oa, stage + kM * kKC + oa);
+                    split_store(r[u][1], stage + ob, stage + kM * kKC + ob);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                    if (remaining_fetch > 0) fetch(r[u]);
+                    stage += 2 * kM * kKC;
+                    if (++s == nstages) { s = 0; par ^= 1u; stage = stages; }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issuer (lane 0 issues; the warp stays converged)
+        constexpr uint32_t idesc = make_idesc(kM, NT);
+        const uint32_t sbo_b = (uint32_t)kq4 * 128u;
+        int s = 0;
+        uint32_t par = 0;
+        for (long j = 0; j < my_tiles; ++j) {
+            const int b = (int)(j & 1);
+            mbar_wait(&tempty[b], (uint32_t)(((j >> 1) & 1) ^ 1));
+            tc_fence_after();
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(&full[s], par);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(stages + (size_t)s * (2 * kM * kKC)), a_lo = a_hi + kM * kKC * 4;
+                    const uint32_t b_hi = smem_u32(Bhi) + (uint32_t)c * (kKC / 4) * 128u;
+                    const uint32_t b_lo = smem_u32(Blo) + (uint32_t)c * (kKC / 4) * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < kKC / 8; ++ks) {
+                        const uint64_t ah = make_desc(a_hi + ks * 256, 128, kSBO);
+                        const uint64_t al = make_desc(a_lo + ks * 256, 128, kSBO);
+                        const uint64_t bh = make_desc(b_hi + ks * 256, 128, sbo_b);
+                        const uint64_t bl = make_desc(b_lo + ks * 256, 128, sbo_b);
+                        mma_tf32(tmem + b * NT, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32(tmem + b * NT, ah, bl, idesc, 1);
+                        mma_tf32(tmem + b * NT, al, bh, idesc, 1);
+                    }
+                    mma_commit(&empty[s]);
+                    if (c == nchunks - 1) mma_commit(&tfull[b]);
+                }
+                __syncwarp();
+                if (++s == nstages) { s = 0; par ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warp w owns accumulator rows 32w..32w+31)
+        float *panel = panels + warp * 32 * kPanelPitch;
+        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+        double acc1[NT / 32], acc2[NT / 32];
+#pragma unroll
+        for (int q = 0; q < NT / 32; ++q) { acc1[q] = 0.0; acc2[q] = 0.0; }
+        // whole launch: every column of the window is valid and rows of C can take 16-byte stores
+        const bool fast_cols = (nvalid == NT) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C + n0) & 15u) == 0);
+        const int pr = lane >> 3, pc = (lane & 7) * 4;            // coalesced read-back: 4 rows x 128 bytes per instruction
+        const long step = 4 * ldc;
+        for (long j = 0; j < my_tiles; ++j) {
+            const int b = (int)(j & 1);
+            const long row0 = ((long)blockIdx.x + j * gridDim.x) * kM + warp * 32;
+            const int nv = (int)max(0L, min(32L, rows - row0));
+            mbar_wait(&tfull[b], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            if (fast_cols && nv == 32) {
+                // ---- full tile: no bounds logic, loads and stores batched (a serial LDS -> STG chain per row costs
+                // ~100 cycles x 32 rows x 4 column groups and made this warp the pipeline's slowest stage)
+                float *dst = C + (row0 + pr) * ldc + n0 + pc;
+#pragma unroll
+                for (int q = 0; q < NT / 32; ++q) {
+                    float v[32];
+                    tmem_ld32(tmem + lane_sel + b * NT + q * 32, v);
+                    if (q == NT / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[b]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4 *>(panel + lane * kPanelPitch + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    __syncwarp();
+                    if (stats != nullptr) {
+                        // 32 rows in fp32 (4 independent chains), widened to fp64 before they meet other tiles
+                        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float x = panel[rr * kPanelPitch + lane];
+                            s1[rr & 3] += x;
+                            s2[rr & 3] = fmaf(x, x, s2[rr & 3]);
+                        }
+                        acc1[q] += (double)((s1[0] + s1[1]) + (s1[2] + s1[3]));
+                        acc2[q] += (double)((s2[0] + s2[1]) + (s2[2] + s2[3]));
+                    }
+                    float4 x[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        x[it] = *reinterpret_cast<const float4 *>(panel + (it * 4 + pr) * kPanelPitch + pc);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        *reinterpret_cast<float4 *>(dst + it * step + q * 32) = x[it];
+                    __syncwarp();
+                }
+                continue;
+            }
+#pragma unroll
+            for (int q = 0; q < NT / 32; ++q) {
+                float v[32];
+                tmem_ld32(tmem + lane_sel + b * NT + q * 32, v);
+                if (q == NT / 32 - 1) {                           // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[b]);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4 *>(panel + lane * kPanelPitch + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                __syncwarp();
+                const int col = q * 32 + lane;                    // column inside this launch's window
+                if (stats != nullptr && nv > 0 && col < nvalid) {
+                    const float shift = panel[lane];
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int rr = 0; rr < nv; ++rr) {
+                        const float dlt = panel[rr * kPanelPitch + lane] - shift;
+                        s1 += dlt;
+                        s2 = fmaf(dlt, dlt, s2);
+                    }
+                    const double sh = (double)shift, d1 = (double)s1;
+                    acc1[q] += d1 + nv * sh;
+                    acc2[q] += (double)s2 + 2.0 * sh * d1 + nv * sh * sh;
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3), c4 = (lane & 7) * 4;
+                    const int gc = q * 32 + c4;
+                    if (rr < nv && gc < nvalid) {
+                        const float4 x = *reinterpret_cast<const float4 *>(panel + rr * kPanelPitch + c4);
+                        float *dst = C + (row0 + rr) * ldc + n0 + gc;
+                        if (gc + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                            *reinterpret_cast<float4 *>(dst) = x;
+                        } else {
+                            dst[0] = x.x;
+                            if (gc + 1 < nvalid) dst[1] = x.y;
+                            if (gc + 2 < nvalid) dst[2] = x.z;
+                            if (gc + 3 < nvalid) dst[3] = x.w;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (stats != nullptr) {
+#pragma unroll
+            for (int q = 0; q < NT / 32; ++q) {
+                const int col = q * 32 + lane;
+                if (col < nvalid) {
+                    atomicAdd(stats + n0 + col, acc1[q]);
+                    atomicAdd(stats + n + n0 + col, acc2[q]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols(2 * NT)) : "memory");
+}
+
+inline bool persist_enabled() {            // PASNL_GEMM_PERSIST=0 forces the one-tile-per-CTA kernel (A/B measurements)
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("PASNL_GEMM_PERSIST");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+inline int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+constexpr long kSmemBudget = 227 * 1024 - 2048;   // opt-in maximum minus the static barriers / slack
+
+// operand stages that fit next to the resident weights and the panels (the kernel needs at least 2)
+inline int persist_stages(int kpad, int nt) {
+    const long fixed = 8L * nt * kpad + 4L * 4 * 32 * kPanelPitch;
+    long st = (kSmemBudget - fixed) / (long)(sizeof(float) * 2 * kM * kKC);
+    if (st > kMaxStages) st = kMaxStages;
+    return (int)st;
+}
+
+template <int NT>
+int launch_persist(long rows, int k, int n, int n0, int nvalid, const float *A, long lda, const float *Bt, long ldb,
+                   float *C, long ldc, double *stats, cudaStream_t st) {
+    const int kpad = (k + kKC - 1) / kKC * kKC;
+    const int nstages = persist_stages(kpad, NT);
+    const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(Bt) & 15u) == 0);
+    const size_t smem = 8UL * NT * kpad + sizeof(float) * ((size_t)nstages * 2 * kM * kKC + 4 * 32 * kPanelPitch);
+    const long ntiles = (rows + kM - 1) / kM;
+    const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    auto kern = gemm_rows_persist_kernel<NT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, kPThreads, smem, st>>>(rows, k, kpad, n, n0, nvalid, ntiles, nstages, A, lda, Bt, ldb, C, ldc, stats,
+                                        vec ? 1 : 0);
+    return pasnl_launch_status();
+}
+
+inline int launch_persist_cols(long rows, int k, int n, int n0, int nvalid, const float *A, long lda, const float *Bt,
+                               long ldb, float *C, long ldc, double *stats, cudaStream_t st) {
+    if (nvalid <= 32) return launch_persist<32>(rows, k, n, n0, nvalid, A, lda, Bt, ldb, C, ldc, stats, st);
+    if (nvalid <= 64) return launch_persist<64>(rows, k, n, n0, nvalid, A, lda, Bt, ldb, C, ldc, stats, st);
+    if (nvalid <= 128) return launch_persist<128>(rows, k, n, n0, nvalid, A, lda, Bt, ldb, C, ldc, stats, st);
+    return launch_persist<160>(rows, k, n, n0, nvalid, A, lda, Bt, ldb, C, ldc, stats, st);
 }
 
 // ================================================================ weight-gradient GEMM:  dW[m, n] = sum_r X[r, m] * Y[r, n]
@@ -515,6 +868,14 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
     if (rows == 0) return PASNL_OK;
     PASNL_CHECK_ARG(A && Bt && C && rows / 128 < 2147483647L && n <= 256 * 65535);
     cudaStream_t st = (cudaStream_t)stream;
+    // many row tiles per SM and small weights: persistent kernel with the weights resident in shared memory
+    // (one launch covers up to 160 output columns, so the 134-wide grouped-feature layers stay single-pass)
+    const int kpad = (k + gtc::kKC - 1) / gtc::kKC * gtc::kKC;
+    if (gtc::persist_enabled() && rows >= 2L * gtc::kM * gtc::sm_count() && n <= 160) {
+        const int nt = n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 160));
+        if (gtc::persist_stages(kpad, nt) >= 2)
+            return gtc::launch_persist_cols(rows, k, n, 0, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
+    }
     // UMMA N must be a multiple of 16 (M = 128): the tile is padded in shared memory, stores are bounds-checked
     if (n <= 32) return gtc::launch<32>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
     if (n <= 64) return gtc::launch<64>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);

@@ -18,6 +18,7 @@ def reference_layer(x, w, b, gamma, beta, act):
 
 
 @pytest.mark.parametrize("shape,cout,act", [((4, 128, 64, 134), 128, 1), ((8, 512, 32, 9), 64, 1), ((32, 1536), 512, 1),
+                                            ((5, 128, 64, 134), 128, 0), ((3, 511, 32, 64), 70, 2),   # (act 0: no ReLU-kink flips among 5M outputs)
                                             ((3, 50, 7, 35), 66, 0), ((2, 777, 5), 3, 2), ((6, 40, 1, 2048), 128, 1)])
 def test_fused_dense_bn_act_forward_backward(cuda, shape, cout, act):
     from pointasnl_b200 import _ops
@@ -66,7 +67,10 @@ def test_tf_util_layers_take_the_fused_path_and_match_op_by_op(cuda):
 
 
 @pytest.mark.parametrize("rows,k,n", [(4096, 64, 64), (16384, 128, 128), (5000, 134, 128), (8192, 9, 64), (2048, 3, 32),
-                                      (1024, 2048, 128), (4096, 259, 256), (3000, 512, 1024), (777, 70, 48), (600, 131, 40)])
+                                      (1024, 2048, 128), (4096, 259, 256), (3000, 512, 1024), (777, 70, 48), (600, 131, 40),
+                                      # >= 2 row tiles per SM with small weights: the persistent weights-resident kernel
+                                      (40000, 128, 128), (50001, 134, 128), (65536, 9, 64), (38017, 3, 32),
+                                      (45000, 128, 134), (40000, 64, 200), (39000, 144, 16), (41000, 70, 48), (40001, 100, 150)])
 def test_tcgen05_gemm_rows_is_fp32_accurate(cuda, rows, k, n):
     """C = A.Bt^T through pasnl_gemm_rows_tf32x3 (3xTF32 on tcgen05) against fp64, held to the same 1e-4 bar as the
     rest of the path; a plain single-pass TF32 product would miss it by ~10x."""
