@@ -420,7 +420,8 @@ def gemm_wgrad(x, dy):
     problems, cuBLAS otherwise."""
     rows, m = x.shape
     n = dy.shape[1]
-    # the UMMA tile is 128 wide in m: inputs with a handful of channels (xyz: 3, 6, 9) would be >90 % padding
+    # inputs with a handful of channels (xyz: 3, 6, 9) stay on cuBLAS: measured 120 us vs 145-165 us on tcgen05 for
+    # 524288 x {3, 9} (the reduction is long but there is almost no reuse to exploit)
     if rows < 4096 or m < 32 or (rows < 16384 and m >= 512) or not x.is_cuda or GEMM_IMPL != "tc":
         return torch.mm(x.t(), dy)
     if x.stride(1) != 1:

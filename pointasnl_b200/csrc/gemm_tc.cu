@@ -849,19 +849,9 @@ __global__ void __launch_bounds__(kThreads) gemm_wgrad_kernel(long rows, int m, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols(NT)) : "memory");
 }
 
-// ---------------------------------------------------------------- warp-specialised weight-gradient kernel
-// Roles: warps 0..3 epilogue, warp 4 MMA issue, warps 5..20 producers, over a ring of operand stages; one CTA per SM
-// walks its row slab.  Producer lanes are laid out 4 rows x 8 column groups, so a warp load covers 4 complete
-// 128-byte lines, and after the 4x4 lane transpose lane l holds column block*32 + l: the STS.128 of a warp fills
-// 4 x 128 contiguous bytes.  A producer warp owns one (4 rows x 32 columns) piece of X and one of Y per chunk -- the
-// transpose is a serial shuffle/select chain, so the work is spread over 16 warps rather than 8.
-// The slab is accumulated in sub-slabs of 1024 rows that alternate between two TMEM accumulators: the epilogue warps
-// add a finished sub-slab into dW while the next one is being accumulated (the TMEM adder truncates, ~7e-9 relative
-// per accumulated row, so partial sums are kept short).
-constexpr int kWPrefetch = 3;
-constexpr int kWProducerWarps = 16;
-constexpr int kWThreads = (5 + kWProducerWarps) * 32;
-constexpr int kSubChunks = 64;     // 64 x 16 = 1024 rows per TMEM accumulation
+// ---------------------------------------------------------------- helpers of the long-reduction weight-gradient kernel
+constexpr int kSubChunks = 64;     // 64 x 16 = 1024 rows per TMEM accumulation (the TMEM adder truncates: ~7e-9
+                                   // relative per accumulated row, so partial sums are kept short)
 
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
     // for warps that wait most of the kernel: poll with back-off instead of spinning on the barrier
@@ -879,195 +869,6 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) 
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kWThreads, 1)
-gemm_wgrad_ws_kernel(long rows, int m, int n, long slab, int nstages, const float *__restrict__ X, long ldx,
-                     const float *__restrict__ Y, long ldy, float *__restrict__ dW, long ldw, int vec4) {
-    constexpr int kStage = 2 * kRC * kM + 2 * kRC * NT;          // floats: X hi | X lo | Y hi | Y lo
-    extern __shared__ __align__(128) float smem[];
-    __shared__ uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
-    __shared__ uint32_t tmem_slot;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int m0 = blockIdx.y * kM, n0 = blockIdx.z * NT;
-    const long r_begin = (long)blockIdx.x * slab, r_end = min(rows, r_begin + slab);
-    if (r_begin >= r_end) return;
-
-    if (t == 0) {
-        for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], kWProducerWarps); mbar_init(&empty[s], 1); }
-        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
-        fence_mbar_init();
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                     "r"(tmem_cols(2 * NT))
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    const int nchunks = (int)((r_end - r_begin + kRC - 1) / kRC);
-    const int nsub = (nchunks + kSubChunks - 1) / kSubChunks;
-
-    if (warp >= 5) {
-        // ------------------------------------------------------------------ producers
-        const int pw = warp - 5;
-        const int r4 = lane & 3, cq = lane >> 2;
-        const int rb4 = pw & 3;                                   // which 4 of the chunk's 16 rows this warp loads
-        const int cb = pw >> 2;                                   // which 32-column block (0..3)
-        const bool yactive = cb * 32 < NT;                        // narrower Y tiles have fewer column blocks
-        const int nfull = (int)((r_end - r_begin) / kRC);         // chunks with all 16 rows inside the slab
-        const long rowoff = r_begin + rb4 * 4 + r4;
-        const int xc = m0 + cb * 32 + cq * 4, yc = n0 + cb * 32 + cq * 4;
-        const float *px = X + rowoff * ldx + xc;
-        const float *py = Y + rowoff * ldy + yc;
-        const bool xv = vec4 && xc + 3 < m, yv = vec4 && yactive && yc + 3 < n;   // constant over the slab
-        const int off = tile_off(cb * 32 + lane, rb4);           // after the transpose: row mn = cb*32 + lane, k group rb4
-        float4 rx[kWPrefetch], ry[kWPrefetch];
-        int fc = 0;                                               // next chunk to fetch
-        auto fetch = [&](float4 &dx, float4 &dy) {
-            const bool fullc = fc < nfull;
-            const long row = rowoff + (long)fc * kRC;
-            dx = (fullc && xv) ? __ldg(reinterpret_cast<const float4 *>(px)) : load4<false>(X, row, r_end, ldx, xc, m);
-            dy = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yactive) dy = (fullc && yv) ? __ldg(reinterpret_cast<const float4 *>(py)) : load4<false>(Y, row, r_end, ldy, yc, n);
-            px += kRC * ldx;
-            py += kRC * ldy;
-            ++fc;
-        };
-        const bool b0 = lane & 1, b1 = lane & 2;
-        auto transpose_split_store = [&](float4 x, float *hi, float *lo) {
-            float v0 = x.x, v1 = x.y, v2 = x.z, v3 = x.w;        // 4 consecutive columns at ONE row (r4)
-            {
-                const float s0 = b0 ? v0 : v1, s1 = b0 ? v2 : v3;
-                const float g0 = __shfl_xor_sync(FULL_MASK, s0, 1), g1 = __shfl_xor_sync(FULL_MASK, s1, 1);
-                if (b0) { v0 = g0; v2 = g1; } else { v1 = g0; v3 = g1; }
-            }
-            {
-                const float s0 = b1 ? v0 : v2, s1 = b1 ? v1 : v3;
-                const float g0 = __shfl_xor_sync(FULL_MASK, s0, 2), g1 = __shfl_xor_sync(FULL_MASK, s1, 2);
-                if (b1) { v0 = g0; v1 = g1; } else { v2 = g0; v3 = g1; }
-            }
-            // now ONE column (block*32 + lane) at 4 consecutive rows: one 16-byte core-matrix row
-            float4 hh, ll;
-            hh.x = tf32_hi(v0); hh.y = tf32_hi(v1); hh.z = tf32_hi(v2); hh.w = tf32_hi(v3);
-            ll.x = v0 - hh.x; ll.y = v1 - hh.y; ll.z = v2 - hh.z; ll.w = v3 - hh.w;
-            *reinterpret_cast<float4 *>(hi) = hh;
-            *reinterpret_cast<float4 *>(lo) = ll;
-        };
-#pragma unroll
-        for (int u = 0; u < kWPrefetch; ++u)
-            if (fc < nchunks) fetch(rx[u], ry[u]);
-        int s = 0;
-        uint32_t par = 1;
-        float *stage = smem;
-        for (int left = nchunks; left > 0; left -= kWPrefetch) {
-#pragma unroll
-            for (int u = 0; u < kWPrefetch; ++u) {
-                if (u < left) {
-                    mbar_wait(&empty[s], par);
-                    float *Xhi = stage, *Xlo = Xhi + kRC * kM, *Yhi = Xlo + kRC * kM, *Ylo = Yhi + kRC * NT;
-                    transpose_split_store(rx[u], Xhi + off, Xlo + off);
-                    if (yactive) transpose_split_store(ry[u], Yhi + off, Ylo + off);   // warp-uniform branch
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[s]);
-                    if (fc < nchunks) fetch(rx[u], ry[u]);
-                    stage += kStage;
-                    if (++s == nstages) { s = 0; par ^= 1u; stage = smem; }
-                }
-            }
-        }
-    } else if (warp == 4) {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc(kM, NT);
-        int s = 0;
-        uint32_t par = 0;
-        for (int i = 0; i < nchunks; ++i) {
-            const int sub = i / kSubChunks, ci = i - sub * kSubChunks, b = sub & 1;
-            if (ci == 0) {
-                mbar_wait(&tempty[b], (uint32_t)(((sub >> 1) & 1) ^ 1));
-                tc_fence_after();
-            }
-            mbar_wait(&full[s], par);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t x_hi = smem_u32(smem + (size_t)s * kStage), x_lo = x_hi + kRC * kM * 4;
-                const uint32_t y_hi = x_lo + kRC * kM * 4, y_lo = y_hi + kRC * NT * 4;
-#pragma unroll
-                for (int ks = 0; ks < kRC / 8; ++ks) {
-                    const uint64_t ah = make_desc(x_hi + ks * 256, 128, kSBO);
-                    const uint64_t al = make_desc(x_lo + ks * 256, 128, kSBO);
-                    const uint64_t bh = make_desc(y_hi + ks * 256, 128, kSBO);
-                    const uint64_t bl = make_desc(y_lo + ks * 256, 128, kSBO);
-                    mma_tf32(tmem + b * NT, ah, bh, idesc, (ci > 0 || ks > 0) ? 1u : 0u);
-                    mma_tf32(tmem + b * NT, ah, bl, idesc, 1);
-                    mma_tf32(tmem + b * NT, al, bh, idesc, 1);
-                }
-                mma_commit(&empty[s]);
-                if (ci == kSubChunks - 1 || i == nchunks - 1) mma_commit(&tfull[b]);
-            }
-            __syncwarp();
-            if (++s == nstages) { s = 0; par ^= 1u; }
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue: add finished sub-slabs into dW
-        const int mrow = m0 + warp * 32 + lane;
-        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-        for (int sub = 0; sub < nsub; ++sub) {
-            const int b = sub & 1;
-            mbar_wait_sleep(&tfull[b], (uint32_t)((sub >> 1) & 1));
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem + lane_sel + b * NT + c0, v);
-                if (mrow < m) {
-                    float *dst = dW + (long)mrow * ldw + n0 + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (n0 + c0 + i < n) atomicAdd(dst + i, v[i]);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[b]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols(2 * NT)) : "memory");
-}
-
-template <int NT>
-int launch_wgrad_ws(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW, long ldw,
-                    cudaStream_t st) {
-    const bool vec = (ldx % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(Y) & 15u) == 0);
-    const size_t stage_bytes = sizeof(float) * (size_t)(2 * kRC * kM + 2 * kRC * NT);
-    int nstages = (int)(kSmemBudget / (long)stage_bytes);
-    if (nstages > kMaxStages) nstages = kMaxStages;
-    const size_t smem = stage_bytes * nstages;
-    const int mt = (m + kM - 1) / kM, nt = (n + NT - 1) / NT;
-    long want = sm_count() / ((long)mt * nt);                    // one CTA per SM over all (m, n) tiles
-    if (want < 1) want = 1;
-    long slab = (rows + want - 1) / want;
-    if (slab < 256) slab = 256;
-    slab = (slab + kRC - 1) / kRC * kRC;
-    const long slabs = (rows + slab - 1) / slab;
-    dim3 grid((unsigned)slabs, (unsigned)mt, (unsigned)nt);
-    cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
-    if (e != cudaSuccess) return (int)e;
-    auto kern = gemm_wgrad_ws_kernel<NT>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    kern<<<grid, kWThreads, smem, st>>>(rows, m, n, slab, nstages, X, ldx, Y, ldy, dW, ldw, vec ? 1 : 0);
-    return pasnl_launch_status();
-}
-
 // ---------------------------------------------------------------- weight gradient with one operand fed through TMEM
 // The L1/shared-memory data pipe is what bounds the kernels above (~0.7 wavefronts per clock per SM for STS + the
 // tensor core's own operand reads).  For dW = X^T.Y both operands arrive [row][column] with the columns contiguous, so
@@ -1076,25 +877,25 @@ int launch_wgrad_ws(long rows, int m, int n, const float *X, long ldx, const flo
 // transpose, no shared memory and no tensor-core shared-memory reads at all.  Only the other operand ("Q") is
 // transposed into K-major shared-memory tiles.  D[p][q] = sum_r P[r][p0+p] * Q[r][q0+q]:
 //   warps 0..3   epilogue (TMEM quadrant w): add finished 1024-row sub-slabs into dW
-//   warps 4..7   P producers (quadrant w-4): 16 coalesced LDG.32 per chunk -> hi/lo -> 2 x tcgen05.st.32x32b.x16
-//   warp  8      MMA issue: tcgen05.mma (A from TMEM, B descriptor), 2 k-steps x (hi.hi, hi.lo, lo.hi) per 16-row chunk
-//   warps 9..16  Q producers: 4 rows x 128-byte loads, 4x4 lane transpose, split, STS.128 into the stage ring
-constexpr int kTThreads = 17 * 32;
-constexpr int kTQWarps = 8, kTPWarps = 4;
+//   warps 4..11  P producers (quadrant (w-4)%4, rows 8*((w-4)/4).. of each chunk): 8 coalesced LDG.32 -> hi/lo ->
+//                2 x tcgen05.st.32x32b.x8
+//   warp  12     MMA issue: tcgen05.mma (A from TMEM, B descriptor), 2 k-steps x (hi.hi, hi.lo, lo.hi) per 16-row chunk
+//   warps 13..20 Q producers: 4 rows x 128-byte loads, 4x4 lane transpose, split, STS.128 into the stage ring
+constexpr int kTThreads = 21 * 32;
+constexpr int kTQWarps = 8, kTPWarps = 8;
+constexpr int kTMmaWarp = 4 + kTPWarps, kTQWarp0 = kTMmaWarp + 1;
 constexpr int kTMaxNQ = 160;                 // two accumulators of <= 160 columns + 6 x 32 ring columns = 512
 constexpr int kTRingCol = 2 * kTMaxNQ;
 constexpr int kTMaxStages = 6;
 constexpr int kTQItems = 3;                  // (4 rows x 32 columns) pieces of Q per producer warp and chunk (5 blocks max)
-constexpr int kTPPrefetch = 2, kTQPrefetch = 3;
+constexpr int kTPPrefetch = 4, kTQPrefetch = 2;
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
         ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
           "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
-          "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+          "r"(__float_as_uint(v[7]))
         : "memory");
 }
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -1127,7 +928,7 @@ gemm_wgrad_tm_kernel(long rows, long slab, int nstages, const float *__restrict_
         mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
         fence_mbar_init();
     }
-    if (warp == 8) {
+    if (warp == kTMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -1140,9 +941,9 @@ gemm_wgrad_tm_kernel(long rows, long slab, int nstages, const float *__restrict_
     const int nfull = (int)((r_end - r_begin) / kRC);             // chunks with all 16 rows inside the slab
     const int nsub = (nchunks + kSubChunks - 1) / kSubChunks;
 
-    if (warp >= 9) {
+    if (warp >= kTQWarp0) {
         // ------------------------------------------------------------------ Q producers (transpose through registers)
-        const int pw = warp - 9;
+        const int pw = warp - kTQWarp0;
         const int r4 = lane & 3, cq = lane >> 2;
         const int rb4 = pw & 3, cbase = pw >> 2;                  // rows rb4*4.. of the chunk; column blocks cbase + 2j
         const int ncb = (nq + 31) >> 5;
@@ -1218,7 +1019,7 @@ gemm_wgrad_tm_kernel(long rows, long slab, int nstages, const float *__restrict_
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kTMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer (A operand from TMEM)
         const uint32_t idesc = make_idesc(kM, nq);
         int s = 0;
@@ -1251,24 +1052,24 @@ gemm_wgrad_tm_kernel(long rows, long slab, int nstages, const float *__restrict_
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ P producers (registers -> TMEM, no transpose)
-        const int quad = warp - 4;
+        const int quad = (warp - 4) & 3, half = (warp - 4) >> 2;  // TMEM quadrant; rows 8*half.. of every chunk
         const int pcol = p0 + quad * 32 + lane;
         const bool valid = pcol < pcols;
         const bool any_valid = p0 + quad * 32 < pcols;            // warp-uniform: quadrants past the matrix only keep the barrier protocol
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-        const float *pp = P + r_begin * ldp + pcol;
-        float rp[kTPPrefetch][16];
+        const float *pp = P + (r_begin + half * 8) * ldp + pcol;
+        float rp[kTPPrefetch][8];
         int fc = 0;
-        auto fetch = [&](float (&d)[16]) {
+        auto fetch = [&](float (&d)[8]) {
             if (any_valid) {
-                const long row0 = r_begin + (long)fc * kRC;
+                const long row0 = r_begin + (long)fc * kRC + half * 8;
                 if (fc < nfull && valid) {
                     const float *a = pp;
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) { d[r] = __ldg(a); a += ldp; }
+                    for (int r = 0; r < 8; ++r) { d[r] = __ldg(a); a += ldp; }
                 } else {
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) d[r] = (valid && row0 + r < r_end) ? __ldg(pp + r * ldp) : 0.f;
+                    for (int r = 0; r < 8; ++r) d[r] = (valid && row0 + r < r_end) ? __ldg(pp + r * ldp) : 0.f;
                 }
             }
             pp += kRC * ldp;
@@ -1286,12 +1087,12 @@ gemm_wgrad_tm_kernel(long rows, long slab, int nstages, const float *__restrict_
                     mbar_wait(&empty[s], par);
                     tc_fence_after();
                     if (any_valid) {
-                        float hi[16], lo[16];
+                        float hi[8], lo[8];
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) { hi[r] = tf32_hi(rp[u][r]); lo[r] = rp[u][r] - hi[r]; }
-                        const uint32_t ta = tmem + lane_sel + kTRingCol + s * 32;
-                        tmem_st16(ta, hi);
-                        tmem_st16(ta + 16, lo);
+                        for (int r = 0; r < 8; ++r) { hi[r] = tf32_hi(rp[u][r]); lo[r] = rp[u][r] - hi[r]; }
+                        const uint32_t ta = tmem + lane_sel + kTRingCol + s * 32 + half * 8;
+                        tmem_st8(ta, hi);
+                        tmem_st8(ta + 16, lo);
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     }
                     tc_fence_before();
@@ -1332,7 +1133,7 @@ gemm_wgrad_tm_kernel(long rows, long slab, int nstages, const float *__restrict_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    if (warp == kTMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 // dW[m][n] = X^T.Y with P = the operand that goes through TMEM (<= 128 columns per tile), Q = the transposed one
@@ -1430,14 +1231,12 @@ extern "C" int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, 
         cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
         return (int)e;
     }
-    // long reductions: one warp-specialised CTA per SM; short ones keep the several-CTAs-per-SM kernel
+    // long reductions: one warp-specialised CTA per SM with one operand fed through TMEM; short ones keep the
+    // several-CTAs-per-SM kernel
     const int ntile = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
     const long tiles = (long)((m + gtc::kM - 1) / gtc::kM) * ((n + ntile - 1) / ntile);
-    if (gtc::persist_enabled() && rows * tiles >= 256L * gtc::sm_count()) {
-        if (gtc::wgrad_tm_enabled()) return gtc::launch_wgrad_tm(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
-        if (n <= 32) return gtc::launch_wgrad_ws<32>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
-        if (n <= 64) return gtc::launch_wgrad_ws<64>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
-        return gtc::launch_wgrad_ws<128>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
+    if (gtc::persist_enabled() && gtc::wgrad_tm_enabled() && rows * tiles >= 256L * gtc::sm_count()) {
+        return gtc::launch_wgrad_tm(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
     }
     if (n <= 32) return gtc::launch_wgrad<32>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
     if (n <= 64) return gtc::launch_wgrad<64>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
