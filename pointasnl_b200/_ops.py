@@ -420,9 +420,10 @@ def gemm_wgrad(x, dy):
     problems, cuBLAS otherwise."""
     rows, m = x.shape
     n = dy.shape[1]
-    # inputs with a handful of channels (xyz: 3, 6, 9) stay on cuBLAS: measured 120 us vs 145-165 us on tcgen05 for
-    # 524288 x {3, 9} (the reduction is long but there is almost no reuse to exploit)
-    if rows < 4096 or m < 32 or (rows < 16384 and m >= 512) or not x.is_cuda or GEMM_IMPL != "tc":
+    # operands with a handful of columns (xyz: 3, 6, 9 channels) take the library's fp32 streaming kernel; 17..31
+    # columns would be mostly padding in a 128-wide UMMA tile and stay on cuBLAS
+    narrow = min(m, n) <= 16
+    if rows < 4096 or (m < 32 and not narrow) or (rows < 16384 and m >= 512) or not x.is_cuda or GEMM_IMPL != "tc":
         return torch.mm(x.t(), dy)
     if x.stride(1) != 1:
         x = x.contiguous()

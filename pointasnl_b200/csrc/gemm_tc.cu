@@ -1199,6 +1199,97 @@ int launch_wgrad(long rows, int m, int n, const float *X, long ldx, const float 
     return pasnl_launch_status();
 }
 
+// ---------------------------------------------------------------- weight gradient with one NARROW operand (<= 16 columns)
+// dW = X^T.Y where X (xyz / normals: 3, 6, 9 channels) or Y has a handful of columns.  A 128-wide UMMA tile would be
+// >90 % padding and cuBLAS runs these at ~1.2 TB/s; the job is one streaming pass over the wide operand, so it is plain
+// fp32 SIMT: thread = (4 columns of the wide operand, one of 16 row lanes), the narrow operand's row is a broadcast load.
+//   out[s * os + w * ow] += sum_r S[r][s] * W[r][w]
+template <int MP>
+__global__ void __launch_bounds__(256) wgrad_narrow_kernel(long rows, long slab, const float *__restrict__ S, long lds,
+                                                           int scols, const float *__restrict__ W, long ldw_, int wcols,
+                                                           float *__restrict__ out, long os, long ow, int vec4) {
+    __shared__ float red[8][MP][64];
+    const int t = threadIdx.x, wq = t & 15, rl = t >> 4, warp = t >> 5;
+    const int w0 = blockIdx.y * 64 + wq * 4;
+    const long r0 = (long)blockIdx.x * slab, r1 = min(rows, r0 + slab);
+    float acc[MP][4];
+#pragma unroll
+    for (int i = 0; i < MP; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    const bool wvec = vec4 && (w0 + 3 < wcols);
+    constexpr int U = 2;
+    for (long rb = r0 + rl; rb < r1; rb += 16 * U) {
+        float4 wv[U];
+        float sv[U][MP];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long r = rb + 16 * u;
+            wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < r1) {
+                if (wvec) wv[u] = __ldg(reinterpret_cast<const float4 *>(W + r * ldw_ + w0));
+                else wv[u] = load4<false>(W, r, r1, ldw_, w0, wcols);
+            }
+#pragma unroll
+            for (int i = 0; i < MP; ++i) sv[u][i] = (i < scols && r < r1) ? __ldg(S + r * lds + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+                acc[i][0] = fmaf(sv[u][i], wv[u].x, acc[i][0]);
+                acc[i][1] = fmaf(sv[u][i], wv[u].y, acc[i][1]);
+                acc[i][2] = fmaf(sv[u][i], wv[u].z, acc[i][2]);
+                acc[i][3] = fmaf(sv[u][i], wv[u].w, acc[i][3]);
+            }
+    }
+    // the two row lanes of a warp, then the 8 warps through shared memory, then one atomic per output and CTA
+#pragma unroll
+    for (int i = 0; i < MP; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] += __shfl_xor_sync(FULL_MASK, acc[i][e], 16);
+    if ((t & 16) == 0) {
+#pragma unroll
+        for (int i = 0; i < MP; ++i)
+            *reinterpret_cast<float4 *>(&red[warp][i][wq * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    __syncthreads();
+    for (int o = t; o < scols * 64; o += 256) {
+        const int i = o >> 6, wc = o & 63;
+        const int w = blockIdx.y * 64 + wc;
+        if (w < wcols) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += red[k][i][wc];
+            atomicAdd(out + i * os + w * ow, v);
+        }
+    }
+}
+
+inline int launch_wgrad_narrow(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
+                               long ldw, cudaStream_t st) {
+    const bool s_is_x = m <= n;                                   // the narrow operand
+    const float *S = s_is_x ? X : Y, *Wd = s_is_x ? Y : X;
+    const long lds = s_is_x ? ldx : ldy, ldwide = s_is_x ? ldy : ldx;
+    const int scols = s_is_x ? m : n, wcols = s_is_x ? n : m;
+    const long os = s_is_x ? ldw : 1, ow = s_is_x ? 1 : ldw;
+    const bool vec = (ldwide % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wd) & 15u) == 0);
+    const int wtiles = (wcols + 63) / 64;
+    long want = (4L * sm_count() + wtiles - 1) / wtiles;
+    long slab = (rows + want - 1) / want;
+    if (slab < 256) slab = 256;
+    slab = (slab + 31) / 32 * 32;
+    dim3 grid((unsigned)((rows + slab - 1) / slab), (unsigned)wtiles);
+    cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
+    if (e != cudaSuccess) return (int)e;
+#define PASNL_NARROW(MP) \
+    wgrad_narrow_kernel<MP><<<grid, 256, 0, st>>>(rows, slab, S, lds, scols, Wd, ldwide, wcols, dW, os, ow, vec ? 1 : 0)
+    if (scols <= 4) PASNL_NARROW(4);
+    else if (scols <= 8) PASNL_NARROW(8);
+    else if (scols <= 12) PASNL_NARROW(12);
+    else PASNL_NARROW(16);
+#undef PASNL_NARROW
+    return pasnl_launch_status();
+}
+
 }  // namespace gtc
 
 extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb,
@@ -1231,6 +1322,7 @@ extern "C" int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, 
         cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
         return (int)e;
     }
+    if ((m <= 16 || n <= 16) && rows >= 1024) return gtc::launch_wgrad_narrow(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
     // long reductions: one warp-specialised CTA per SM with one operand fed through TMEM; short ones keep the
     // several-CTAs-per-SM kernel
     const int ntile = n <= 32 ? 32 : (n <= 64 ? 64 : 128);

@@ -5,7 +5,7 @@ import torch
 from pointasnl_b200 import _ops
 from tools.bench_op import timeit
 shapes = [(262144, 128, 128), (262144, 134, 128), (524288, 64, 64), (16384, 2048, 128), (16384, 256, 512), (524288, 9, 64),
-          (524288, 3, 32), (262144, 32, 3), (65536, 128, 128), (16384, 128, 128)]
+          (524288, 3, 32), (262144, 32, 3), (262144, 3, 32), (32768, 3, 64), (16384, 9, 128), (16384, 6, 32)]
 for rows, m, n in shapes:
     x = torch.randn(rows, m, device="cuda"); y = torch.randn(rows, n, device="cuda")
     med, _ = timeit(lambda: _ops.gemm_wgrad(x, y), iters=10)
