@@ -1204,25 +1204,27 @@ int launch_wgrad(long rows, int m, int n, const float *X, long ldx, const float 
 // >90 % padding and cuBLAS runs these at ~1.2 TB/s; the job is one streaming pass over the wide operand, so it is plain
 // fp32 SIMT: thread = (4 columns of the wide operand, one of 16 row lanes), the narrow operand's row is a broadcast load.
 //   out[s * os + w * ow] += sum_r S[r][s] * W[r][w]
-template <int MP>
+template <int MP, int WQ>
 __global__ void __launch_bounds__(256) wgrad_narrow_kernel(long rows, long slab, const float *__restrict__ S, long lds,
                                                            int scols, const float *__restrict__ W, long ldw_, int wcols,
                                                            float *__restrict__ out, long os, long ow, int vec4) {
-    __shared__ float red[8][MP][64];
-    const int t = threadIdx.x, wq = t & 15, rl = t >> 4, warp = t >> 5;
-    const int w0 = blockIdx.y * 64 + wq * 4;
+    // WQ = float4 column groups per row of the wide operand (4, 8 or 16): 256 / WQ rows are in flight per CTA
+    constexpr int RL = 256 / WQ;
+    __shared__ float red[8][MP][WQ * 4];
+    const int t = threadIdx.x, wq = t % WQ, rl = t / WQ, warp = t >> 5;
+    const int w0 = blockIdx.y * (WQ * 4) + wq * 4;
     const long r0 = (long)blockIdx.x * slab, r1 = min(rows, r0 + slab);
     float acc[MP][4];
 #pragma unroll
     for (int i = 0; i < MP; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     const bool wvec = vec4 && (w0 + 3 < wcols);
     constexpr int U = 2;
-    for (long rb = r0 + rl; rb < r1; rb += 16 * U) {
+    for (long rb = r0 + rl; rb < r1; rb += RL * U) {
         float4 wv[U];
         float sv[U][MP];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long r = rb + 16 * u;
+            const long r = rb + RL * u;
             wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < r1) {
                 if (wvec) wv[u] = __ldg(reinterpret_cast<const float4 *>(W + r * ldw_ + w0));
@@ -1241,20 +1243,22 @@ __global__ void __launch_bounds__(256) wgrad_narrow_kernel(long rows, long slab,
                 acc[i][3] = fmaf(sv[u][i], wv[u].w, acc[i][3]);
             }
     }
-    // the two row lanes of a warp, then the 8 warps through shared memory, then one atomic per output and CTA
+    // the row lanes of a warp, then the 8 warps through shared memory, then one atomic per output and CTA
 #pragma unroll
-    for (int i = 0; i < MP; ++i)
+    for (int off = WQ; off < 32; off <<= 1)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[i][e] += __shfl_xor_sync(FULL_MASK, acc[i][e], 16);
-    if ((t & 16) == 0) {
+        for (int i = 0; i < MP; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][e] += __shfl_xor_sync(FULL_MASK, acc[i][e], off);
+    if ((t & 31) < WQ) {
 #pragma unroll
         for (int i = 0; i < MP; ++i)
             *reinterpret_cast<float4 *>(&red[warp][i][wq * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     __syncthreads();
-    for (int o = t; o < scols * 64; o += 256) {
-        const int i = o >> 6, wc = o & 63;
-        const int w = blockIdx.y * 64 + wc;
+    for (int o = t; o < scols * (WQ * 4); o += 256) {
+        const int i = o / (WQ * 4), wc = o % (WQ * 4);
+        const int w = blockIdx.y * (WQ * 4) + wc;
         if (w < wcols) {
             float v = 0.f;
 #pragma unroll
@@ -1272,7 +1276,8 @@ inline int launch_wgrad_narrow(long rows, int m, int n, const float *X, long ldx
     const int scols = s_is_x ? m : n, wcols = s_is_x ? n : m;
     const long os = s_is_x ? ldw : 1, ow = s_is_x ? 1 : ldw;
     const bool vec = (ldwide % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wd) & 15u) == 0);
-    const int wtiles = (wcols + 63) / 64;
+    const int wq = wcols <= 16 ? 4 : (wcols <= 32 ? 8 : 16);      // float4 column groups per row and CTA
+    const int wtiles = (wcols + wq * 4 - 1) / (wq * 4);
     long want = (4L * sm_count() + wtiles - 1) / wtiles;
     long slab = (rows + want - 1) / want;
     if (slab < 256) slab = 256;
@@ -1280,13 +1285,20 @@ inline int launch_wgrad_narrow(long rows, int m, int n, const float *X, long ldx
     dim3 grid((unsigned)((rows + slab - 1) / slab), (unsigned)wtiles);
     cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
     if (e != cudaSuccess) return (int)e;
-#define PASNL_NARROW(MP) \
-    wgrad_narrow_kernel<MP><<<grid, 256, 0, st>>>(rows, slab, S, lds, scols, Wd, ldwide, wcols, dW, os, ow, vec ? 1 : 0)
+#define PASNL_NARROW_WQ(MP, WQ) \
+    wgrad_narrow_kernel<MP, WQ><<<grid, 256, 0, st>>>(rows, slab, S, lds, scols, Wd, ldwide, wcols, dW, os, ow, vec ? 1 : 0)
+#define PASNL_NARROW(MP)                      \
+    do {                                      \
+        if (wq == 4) PASNL_NARROW_WQ(MP, 4);  \
+        else if (wq == 8) PASNL_NARROW_WQ(MP, 8); \
+        else PASNL_NARROW_WQ(MP, 16);         \
+    } while (0)
     if (scols <= 4) PASNL_NARROW(4);
     else if (scols <= 8) PASNL_NARROW(8);
     else if (scols <= 12) PASNL_NARROW(12);
     else PASNL_NARROW(16);
 #undef PASNL_NARROW
+#undef PASNL_NARROW_WQ
     return pasnl_launch_status();
 }
 

@@ -101,7 +101,7 @@ def test_tcgen05_gemm_rows_is_fp32_accurate(cuda, rows, k, n):
                                       (40000, 70, 48), (45003, 131, 64), (524288, 9, 64),
                                       # one narrow operand: fp32 streaming kernel
                                       (100000, 3, 32), (33333, 6, 30), (8192, 9, 128), (70000, 32, 3), (5000, 16, 200),
-                                      (4097, 2, 2)])
+                                      (4097, 2, 2), (300000, 16, 16), (200000, 9, 16), (50000, 13, 24)])
 def test_tcgen05_wgrad_gemm(cuda, rows, m, n):
     """dW = X^T Y through pasnl_gemm_wgrad_tf32x3 (tcgen05, row slabs + reductions) against fp64."""
     from pointasnl_b200 import _ops

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pointasnl_b200 import _ops
 from tools.bench_op import timeit
-shapes = [(262144, 128, 128), (262144, 134, 128), (524288, 64, 64), (16384, 2048, 128), (16384, 256, 512), (524288, 9, 64),
+shapes = [(1310720, 16, 16), (1310720, 9, 16), (262144, 128, 128), (262144, 134, 128), (524288, 64, 64), (16384, 2048, 128), (16384, 256, 512), (524288, 9, 64),
           (524288, 3, 32), (262144, 32, 3), (262144, 3, 32), (32768, 3, 64), (16384, 9, 128), (16384, 6, 32)]
 for rows, m, n in shapes:
     x = torch.randn(rows, m, device="cuda"); y = torch.randn(rows, n, device="cuda")
