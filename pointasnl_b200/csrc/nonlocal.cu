@@ -405,6 +405,19 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 int nl_core_fwd_tcgen05(int b, int s, int n, int d, const float *q, const float *kv, float scale, float *out,
                          float *lse, cudaStream_t st);
 
+// tcgen05 backward (nonlocal_bwd_tc.cu): dQ / (dKf, dV) kernels, after the delta pass
+int nl_core_bwd_tcgen05(int b, int s, int n, int d, const float *q, const float *kv, const float *lse, const float *delta,
+                         float scale, const float *dout, float *gq, float *gkv, cudaStream_t st);
+
+static bool use_tensor_core_bwd(int s, int n, int d) {
+    // PASNL_NL_BWD=simt|tc overrides (profiling / A-B measurements)
+    static const char *force = getenv("PASNL_NL_BWD");
+    if (force && force[0] == 's') return false;
+    if (d != 32) return false;
+    if (force && force[0] == 't') return true;
+    return s >= 64 && n >= 128;
+}
+
 static bool use_tensor_core_path(int s, int n, int d) {
     // A 128-query x 64-key x d tile must be worth filling: tiny problems (deep seg layers: s=40, n=80) and widths the
     // tcgen05 kernel is not instantiated for stay on the CUDA-core kernel.  PASNL_NL_FWD=simt|tc overrides (profiling).
@@ -449,6 +462,11 @@ extern "C" int pasnl_nl_core_bwd(int b, int s, int n, int d, const float *q, con
     PASNL_CHECK_ARG(q && kv && out && lse && grad_out && grad_q && grad_kv && workspace);
     PASNL_CHECK_ARG(aligned16(q) && aligned16(kv) && aligned16(out) && aligned16(grad_out));
     float *delta = (float *)workspace;
+    if (use_tensor_core_bwd(s, n, d) && aligned16(grad_q) && aligned16(grad_kv)) {
+        const long rows = (long)b * s;
+        nl_delta_kernel<<<ceil_div_i(rows, 256), 256, 0, st>>>(rows, d, grad_out, out, delta);
+        return nl_core_bwd_tcgen05(b, s, n, d, q, kv, lse, delta, scale, grad_out, grad_q, grad_kv, st);
+    }
     if (d <= 32) return launch_bwd<32, 64>(b, s, n, d, q, kv, out, lse, scale, grad_out, grad_q, grad_kv, delta, st);
     if (d <= 64) return launch_bwd<64, 64>(b, s, n, d, q, kv, out, lse, scale, grad_out, grad_q, grad_kv, delta, st);
     return launch_bwd<128, 32>(b, s, n, d, q, kv, out, lse, scale, grad_out, grad_q, grad_kv, delta, st);

@@ -330,7 +330,9 @@ def test_as_resample_fwd_bwd_strided_views(cuda, b, s, K, k, cg):
 
 
 # ------------------------------------------------------------------ Non-Local core
-NL_CASES = [(4, 512, 1024, 32), (4, 128, 512, 64), (2, 1280, 2000, 32), (2, 40, 80, 128), (2, 70, 130, 36), (1, 1, 5, 4), (2, 100, 33, 64)]
+NL_CASES = [(4, 512, 1024, 32), (4, 128, 512, 64), (2, 1280, 2000, 32), (2, 40, 80, 128), (2, 70, 130, 36), (1, 1, 5, 4), (2, 100, 33, 64),
+            # d = 32: tcgen05 backward (ragged query / key tails; few query tiles -> key range split with atomics)
+            (3, 200, 333, 32), (1, 130, 4100, 32), (2, 65, 129, 32)]
 
 
 @pytest.mark.parametrize("b,s,n,d", NL_CASES)
