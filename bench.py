@@ -106,6 +106,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ per-kernel model
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+TRAFFIC_NCU = {
+    ("pasnl_gemm_rows_tf32x3", (262144, 128, 128)): 134382080 + 83796736,   # profiles/r01b_ncu_full_gemm_rows_persist_*.csv
+    ("pasnl_gemm_wgrad_tf32x3", (262144, 128, 128)): 268592896,            # profiles/r01b_ncu_full_gemm_wgrad_tm_*.csv
+}
+
+
+def gemm_bound(nbytes, flops):
+    """Which roof a GEMM launch sits under: 3xTF32 issues 3 tensor passes at half the bf16 rate, so the tensor time is
+    6 * flops / bf16_peak; the skinny layers of this path (rows >> k, n) stream their operands and are HBM bound."""
+    pk = load_peaks()
+    t_tensor = 6.0 * flops / (pk["bf16_tflops"] * 1e12)
+    t_hbm = nbytes / (pk["hbm_gbs"] * 1e9)
+    return "tensor" if t_tensor > t_hbm else "hbm"
+
+
 def algorithmic_work(name, a):
     """(bytes, flops, bound) of one launch from its integer arguments (stated in DESIGN.md)."""
     if name == "pasnl_fps":
@@ -163,10 +179,10 @@ def algorithmic_work(name, a):
         return 4 * b * (4 * s * d + 4 * n * d) + 8 * b * s, 10 * b * s * n * d, "tensor"
     if name == "pasnl_gemm_rows_tf32x3":
         rows, k, n = a[0:3]
-        return 4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n, "tensor"
+        return 4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n, gemm_bound(4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n)
     if name == "pasnl_gemm_wgrad_tf32x3":
         rows, m, n = a[0:3]
-        return 4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n, "tensor"
+        return 4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n, gemm_bound(4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n)
     if name == "pasnl_bn_act_fwd":       # stats read + apply read/write of the (rows, c) activation
         rows, c = a[0:2]
         return 12 * rows * c, 8 * rows * c, "hbm"
@@ -413,14 +429,20 @@ def main():
     rows = prof.table(prof_steps)
     eager_ms = ev0.elapsed_time(ev1) / prof_steps
     ours_ms = sum(r["ms_per_step"] for r in rows)
-    top = rows[0]
+    # dominant kernel = the entry point with the largest share of the step, reported on the shape it spends most time on
+    by_name = {}
+    for r in rows:
+        by_name[r["name"]] = by_name.get(r["name"], 0.0) + r["ms_per_step"]
+    top_name = max(by_name, key=by_name.get)
+    top = max((r for r in rows if r["name"] == top_name), key=lambda r: r["ms_per_step"])
     if top["bound"] == "tensor":
         roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": top["tflops"] / peaks["bf16_tflops"]}
     else:
         roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": top["gbs"] / peaks["hbm_gbs"]}
-    roof.update({"traffic": None, "kernel": top["name"], "dims": top["dims"], "avg_us": top["avg_us"],
+    roof.update({"traffic": TRAFFIC_NCU.get((top["name"], tuple(top["dims"]))), "kernel": top["name"], "dims": top["dims"],
+                 "avg_us": top["avg_us"], "entry_point_ms_per_step": by_name[top_name],
                  "native_bound": top["bound"], "peak_source": peaks["src"],
                  "timing": f"CUDA events around each launch, eager pass of {prof_steps} steps",
                  "pasnl_share_of_step": ours_ms / eager_ms if eager_ms > 0 else None})
