@@ -139,6 +139,38 @@ __device__ __forceinline__ void tile_fetch(TileRegs<ROWS> &tr, const float *__re
             tr.v[j] = load4<VEC4>(src, row_base + rg * 8 + r8, row_limit, ld, kb + (kq + 4 * h) * 4, k);
     }
 }
+// The same fetch with the address arithmetic hoisted out of the k loop: one pointer per item, computed once per tile.
+// `fast` = every row of the tile exists and loads are 16-byte aligned; only a ragged last k chunk takes the checked path.
+template <int ROWS>
+struct TilePtrs {
+    const float *p[TileRegs<ROWS>::PER_WARP];
+    bool fast;
+};
+template <int ROWS>
+__device__ __forceinline__ void tile_ptrs(TilePtrs<ROWS> &tp, const float *__restrict__ src, long row_base, long row_limit,
+                                          long ld, bool vec4, int warp, int lane) {
+    static_assert(kKC == 16, "one 16-wide k slab per item");
+    const int r8 = lane & 7, kq = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < TileRegs<ROWS>::PER_WARP; ++j) {
+        const int item = warp + 8 * j;
+        tp.p[j] = src + (row_base + (item % (ROWS / 8)) * 8 + r8) * ld + kq * 4;
+    }
+    tp.fast = vec4 && (row_base + ROWS <= row_limit);
+}
+template <int ROWS, bool VEC4>
+__device__ __forceinline__ void tile_fetch_fast(TileRegs<ROWS> &tr, const TilePtrs<ROWS> &tp, const float *__restrict__ src,
+                                                long row_base, long row_limit, long ld, int kb, int k, int warp, int lane) {
+    if (tp.fast && kb + kKC <= k) {
+#pragma unroll
+        for (int j = 0; j < TileRegs<ROWS>::PER_WARP; ++j) {
+            tr.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (warp + 8 * j < TileRegs<ROWS>::ITEMS) tr.v[j] = __ldg(reinterpret_cast<const float4 *>(tp.p[j] + kb));
+        }
+    } else {
+        tile_fetch<ROWS, VEC4>(tr, src, row_base, row_limit, ld, kb, k, warp, lane);
+    }
+}
 // registers -> split -> shared memory operand tiles.  hi = a & mask, lo = a - hi: one LOP + one FADD per element.
 template <int ROWS>
 __device__ __forceinline__ void tile_store(const TileRegs<ROWS> &tr, float *hi, float *lo, int warp, int lane) {
@@ -209,11 +241,15 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
     // global loads per thread are always in flight (the loop is otherwise one memory latency per chunk)
     TileRegs<kM> ra[2];
     TileRegs<NT> rb[2];
-    tile_fetch<kM, VEC4>(ra[0], A, row0, rows, lda, 0, k, warp, lane);
-    tile_fetch<NT, VEC4>(rb[0], Bt, n0, (long)n0 + nvalid, ldb, 0, k, warp, lane);
+    TilePtrs<kM> pa;
+    TilePtrs<NT> pb;
+    tile_ptrs<kM>(pa, A, row0, rows, lda, VEC4, warp, lane);
+    tile_ptrs<NT>(pb, Bt, n0, (long)n0 + nvalid, ldb, VEC4, warp, lane);
+    tile_fetch_fast<kM, VEC4>(ra[0], pa, A, row0, rows, lda, 0, k, warp, lane);
+    tile_fetch_fast<NT, VEC4>(rb[0], pb, Bt, n0, (long)n0 + nvalid, ldb, 0, k, warp, lane);
     if (nchunks > 1) {
-        tile_fetch<kM, VEC4>(ra[1], A, row0, rows, lda, kKC, k, warp, lane);
-        tile_fetch<NT, VEC4>(rb[1], Bt, n0, (long)n0 + nvalid, ldb, kKC, k, warp, lane);
+        tile_fetch_fast<kM, VEC4>(ra[1], pa, A, row0, rows, lda, kKC, k, warp, lane);
+        tile_fetch_fast<NT, VEC4>(rb[1], pb, Bt, n0, (long)n0 + nvalid, ldb, kKC, k, warp, lane);
     }
     auto step = [&](int i, TileRegs<kM> &rga, TileRegs<NT> &rgb) {
         const int sidx = i & 1;
@@ -226,8 +262,8 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
         tile_store<kM>(rga, Ahi, Alo, warp, lane);
         tile_store<NT>(rgb, Bhi, Blo, warp, lane);
         if (i + 2 < nchunks) {
-            tile_fetch<kM, VEC4>(rga, A, row0, rows, lda, (i + 2) * kKC, k, warp, lane);
-            tile_fetch<NT, VEC4>(rgb, Bt, n0, (long)n0 + nvalid, ldb, (i + 2) * kKC, k, warp, lane);
+            tile_fetch_fast<kM, VEC4>(rga, pa, A, row0, rows, lda, (i + 2) * kKC, k, warp, lane);
+            tile_fetch_fast<NT, VEC4>(rgb, pb, Bt, n0, (long)n0 + nvalid, ldb, (i + 2) * kKC, k, warp, lane);
         }
         fence_async_smem();
         tc_fence_before();
