@@ -68,7 +68,7 @@ profiler = None    # optional object with before(name, args) / after(name, args)
 KERNELS_PER_CALL = {
     "pasnl_gather_point_grad": 2, "pasnl_gather_rows_grad": 2, "pasnl_group_point_grad": 2,
     "pasnl_three_interpolate_grad": 2, "pasnl_group_concat_grad": 4, "pasnl_nl_core_bwd": 3,
-    "pasnl_bn_act_fwd": 4, "pasnl_bn_act_bwd": 3, "pasnl_gemm_wgrad_tf32x3": 2,
+    "pasnl_bn_act_fwd": 3, "pasnl_bn_act_bwd": 3, "pasnl_gemm_wgrad_tf32x3": 2,
 }
 
 

@@ -480,8 +480,8 @@ def gemm_rows(a, bt, col_stats=None):
 
 class DenseBNAct(torch.autograd.Function):
     """act(batch_norm_train(x @ w + bias)) for a 1x1 conv / fully connected layer (tf_util.py:120-185,512-531).
-    The GEMMs are cuBLAS (torch.mm: plain library GEMMs); everything between them is two fused pasnl kernels forward
-    (statistics, normalise+activate) and two backward (reductions, apply).  The bias cancels inside train-mode batch
+    The GEMMs are cuBLAS (torch.mm: plain library GEMMs); everything between them is fused pasnl kernels: forward
+    statistics (inside the GEMM epilogue when it can) and normalise+activate and two backward (reductions, apply).  The bias cancels inside train-mode batch
     norm: it is not added and its gradient is exactly zero."""
 
     @staticmethod

@@ -112,41 +112,39 @@ __global__ void bn_stats_kernel(long rows, int c, int cvec, int rpb, const float
     }
 }
 
-// mean / biased variance from the shifted sums
-__global__ void bn_finalize_kernel(long rows, int c, const float *__restrict__ y, const double *__restrict__ ws,
-                                   float *__restrict__ mean, float *__restrict__ var, const float *__restrict__ bias,
-                                   float *__restrict__ running_mean, float *__restrict__ running_var, float decay,
-                                   int shifted) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
-    const double n = (double)rows;
-    const double m = ws[ch] / n;
-    double v = ws[c + ch] / n - m * m;
-    if (v < 0.0) v = 0.0;
-    const float mu = (float)((shifted ? (double)y[ch] : 0.0) + m);
-    mean[ch] = mu;
-    var[ch] = (float)v;
-    // moving averages as tf.contrib.layers.batch_norm keeps them (assign_moving_average, biased batch variance)
-    if (running_mean) running_mean[ch] = decay * running_mean[ch] + (1.f - decay) * (mu + (bias ? bias[ch] : 0.f));
-    if (running_var) running_var[ch] = decay * running_var[ch] + (1.f - decay) * (float)v;
-}
-
 // out = act((y - mean) * rstd * gamma + beta).  Same (row-lane, channel-group) thread layout as the statistics
 // pass: a thread keeps its channels' parameters in registers and streams rows, so the only memory instructions in
 // the loop are the data loads/stores themselves.
+// The finalisation of the statistics (mean / biased variance from the sums, moving averages) is folded in: every thread
+// derives its channels' mean and variance from the fp64 sums, CTA 0 also publishes them (saved for the backward) and
+// updates the moving averages -- one launch less per layer.
 template <int VEC>
 __global__ void bn_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
-                                const float *__restrict__ mean, const float *__restrict__ var,
-                                const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int act,
-                                float *__restrict__ out) {
+                                const double *__restrict__ ws, int shifted, float *__restrict__ mean,
+                                float *__restrict__ var, const float *__restrict__ bias, float *__restrict__ running_mean,
+                                float *__restrict__ running_var, float decay, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, float eps, int act, float *__restrict__ out) {
     const int t = threadIdx.x, cv = t % cvec, ry = t / cvec;
     const int col = cv * VEC;
     float mu[VEC], sc[VEC], be[VEC];
+    const double n = (double)rows;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        mu[v] = __ldg(mean + col + v);
-        sc[v] = rsqrtf(__ldg(var + col + v) + eps) * __ldg(gamma + col + v);
-        be[v] = __ldg(beta + col + v);
+        const int ch = col + v;
+        const double m = ws[ch] / n;
+        double vv = ws[c + ch] / n - m * m;
+        if (vv < 0.0) vv = 0.0;
+        mu[v] = (float)((shifted ? (double)__ldg(y + ch) : 0.0) + m);
+        const float vf = (float)vv;
+        sc[v] = rsqrtf(vf + eps) * __ldg(gamma + ch);
+        be[v] = __ldg(beta + ch);
+        if (blockIdx.x == 0 && ry == 0) {
+            mean[ch] = mu[v];
+            var[ch] = vf;
+            // moving averages as tf.contrib.layers.batch_norm keeps them (assign_moving_average, biased batch variance)
+            if (running_mean) running_mean[ch] = decay * running_mean[ch] + (1.f - decay) * (mu[v] + (bias ? bias[ch] : 0.f));
+            if (running_var) running_var[ch] = decay * running_var[ch] + (1.f - decay) * vf;
+        }
     }
     const long chunk = (rows + gridDim.x - 1) / gridDim.x;
     const long r0 = (long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
@@ -368,14 +366,12 @@ extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *g
     const int ag = apply_grid(rows, s.rpb);
     if (s.vec == 4) {
         if (!stats_ready) bn_stats_kernel<4><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
-        bn_finalize_kernel<<<ceil_div_i(c, 128), 128, 0, st>>>(rows, c, y, ws, mean, var, bias, running_mean,
-                                                               running_var, decay, stats_ready ? 0 : 1);
-        bn_apply_kernel<4><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, mean, var, gamma, beta, eps, act, out);
+        bn_apply_kernel<4><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, ws, stats_ready ? 0 : 1, mean, var, bias,
+                                                     running_mean, running_var, decay, gamma, beta, eps, act, out);
     } else {
         if (!stats_ready) bn_stats_kernel<1><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
-        bn_finalize_kernel<<<ceil_div_i(c, 128), 128, 0, st>>>(rows, c, y, ws, mean, var, bias, running_mean,
-                                                               running_var, decay, stats_ready ? 0 : 1);
-        bn_apply_kernel<1><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, mean, var, gamma, beta, eps, act, out);
+        bn_apply_kernel<1><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, ws, stats_ready ? 0 : 1, mean, var, bias,
+                                                     running_mean, running_var, decay, gamma, beta, eps, act, out);
     }
     return pasnl_launch_status();
 }
