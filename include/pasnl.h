@@ -180,7 +180,9 @@ int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *gamma, const
 /* Backward of the above: dout (rows, c) -> dy (rows, c) (the gradient w.r.t. the GEMM output), dgamma (c), dbeta (c). */
 int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *dout, const float *gamma, const float *beta,
                      const float *mean, const float *var, float eps, int act, float *dy, float *dgamma, float *dbeta,
-                     void *workspace, void *stream);
+                     int workspace_zeroed, void *workspace, void *stream);
+/* workspace_zeroed != 0: the caller hands in a workspace that is already all-zero (e.g. a slice of one arena cleared
+ * once per training step), the entry point then skips its own memset node. */
 
 /* fp32-accurate GEMM of the 1x1-conv / fully-connected layers on tcgen05 tensor cores (3xTF32 split, fp32 TMEM
  * accumulation; replaces tf.nn.conv2d / tf.matmul of tf_util.py:120-185,318-355 and their input gradients):
@@ -194,9 +196,10 @@ int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, co
 /* Weight gradient of the same layers (replaces the tf.matmul / conv2d filter gradients TF autodiff emits):
  *     dW[m, n] = sum_r X[r, m] * Y[r, n] ,   X (rows, m), Y (rows, n), dW (m, n) row-major, ldw == n.
  * X = layer input, Y = gradient w.r.t. the GEMM output.  tcgen05, 3xTF32, operands transposed on the way into shared memory,
- * row slabs reduced into dW (zero-filled here) with fp32 reductions: results are order-dependent at the 1e-7 level. */
+ * row slabs reduced into dW with fp32 reductions: results are order-dependent at the 1e-7 level.  dW is zero-filled
+ * here unless dw_zeroed != 0 (the caller passes memory that is already all-zero, e.g. a slice of a per-step arena). */
 int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
-                            long ldw, void *stream);
+                            long ldw, int dw_zeroed, void *stream);
 
 #ifdef __cplusplus
 }

@@ -45,10 +45,10 @@ SIGNATURES = {
     "pasnl_nl_core_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pasnl_nl_core_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P]),
     "pasnl_gemm_rows_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),
-    "pasnl_gemm_wgrad_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P]),
+    "pasnl_gemm_wgrad_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, c_int, P]),
     "pasnl_bn_workspace_bytes": (c_size_t, [c_int]),
     "pasnl_bn_act_fwd": (c_int, [c_long, c_int, P, P, P, c_float, c_int, P, P, P, P, P, P, c_float, c_int, P, P]),
-    "pasnl_bn_act_bwd": (c_int, [c_long, c_int, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
+    "pasnl_bn_act_bwd": (c_int, [c_long, c_int, P, P, P, P, P, P, c_float, c_int, P, P, P, c_int, P, P]),
 }
 
 

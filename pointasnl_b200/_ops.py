@@ -429,14 +429,86 @@ def gemm_wgrad(x, dy):
         x = x.contiguous()
     if dy.stride(1) != 1:
         dy = dy.contiguous()
-    dw = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    dw = _zero_arena.zeros((m, n), torch.float32) if (_zero_arena is not None and _zero_arena.device == x.device) else None
+    zeroed = dw is not None
+    if dw is None:
+        dw = torch.empty((m, n), device=x.device, dtype=torch.float32)
     _call("pasnl_gemm_wgrad_tf32x3", rows, m, n, _ptr(x), int(x.stride(0)), _ptr(dy), int(dy.stride(0)), _ptr(dw), n,
-          _stream())
+          1 if zeroed else 0, _stream())
+    if zeroed:
+        _lib.launch_count -= 1          # no memset node was enqueued
     return dw
 
 
 # ------------------------------------------------------------------ dense glue: GEMM + fused BN/activation epilogue
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+class ZeroArena:
+    """One device buffer that is cleared ONCE per training step and handed out in slices wherever the dense glue needs
+    zero-initialised memory (batch-norm statistic accumulators, weight-gradient outputs that are reduced into with
+    atomics, the identically-zero bias gradient).  A 26-layer step otherwise enqueues ~100 separate two-microsecond
+    fill / memset nodes, each one a dependent launch on the critical path.
+
+    Use:  arena = ZeroArena(device);  at the start of every step  `arena.reset()`;  run the step inside
+    `with use_zero_arena(arena):`.  A request the arena cannot serve (first steps, while it is still being sized) falls
+    back to a fresh torch.zeros; `reset()` then grows the buffer to the high-water mark.  Slices stay valid until the
+    next reset(), i.e. gradients must be consumed (copied into the gradient bucket, applied) within the step."""
+
+    ALIGN = 256
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.buf = torch.zeros((0,), dtype=torch.uint8, device=self.device)
+        self.off = 0
+        self.need = 0
+
+    def reset(self):
+        if self.need > self.buf.numel():
+            self.buf = torch.zeros((self.need,), dtype=torch.uint8, device=self.device)
+        else:
+            self.buf.zero_()
+        self.off = 0
+        self.need = 0
+
+    def zeros(self, shape, dtype):
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        span = (nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.need += span
+        if self.off + span > self.buf.numel():
+            return None
+        t = self.buf[self.off:self.off + nbytes].view(dtype).view(shape)
+        self.off += span
+        return t
+
+
+_zero_arena = None
+
+
+class use_zero_arena:
+    def __init__(self, arena):
+        self.arena = arena
+
+    def __enter__(self):
+        global _zero_arena
+        self.prev, _zero_arena = _zero_arena, self.arena
+        return self.arena
+
+    def __exit__(self, *exc):
+        global _zero_arena
+        _zero_arena = self.prev
+
+
+def _zeros(shape, dtype, device):
+    """(tensor, from_arena): zero-initialised memory, from the active arena when there is one."""
+    if _zero_arena is not None and _zero_arena.device == torch.device(device):
+        t = _zero_arena.zeros(tuple(shape), dtype)
+        if t is not None:
+            return t, True
+    return torch.zeros(tuple(shape), dtype=dtype, device=device), False
 
 import os as _os
 
@@ -490,7 +562,7 @@ class DenseBNAct(torch.autograd.Function):
         x2 = x.reshape(-1, cin)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        ws = torch.zeros((2 * cout,), device=x2.device, dtype=torch.float64)
+        ws, _ = _zeros((2 * cout,), torch.float64, x2.device)
         # x.W on tensor cores (3xTF32); the GEMM epilogue also accumulates the batch-norm statistics when it can
         y, stats_ready = gemm_rows(x2, w2d.t().contiguous(), col_stats=ws)
         rows = y.shape[0]
@@ -517,10 +589,15 @@ class DenseBNAct(torch.autograd.Function):
         dy = torch.empty_like(y)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(beta)
-        ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
+        ws = _zero_arena.zeros((2 * cout,), torch.float64) if (_zero_arena is not None and _zero_arena.device == y.device) else None
+        ws_zeroed = ws is not None
+        if ws is None:
+            ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
         _call("pasnl_bn_act_bwd", rows, cout, _ptr(y), _ptr(dout), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), eps,
-              act, _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
+              act, _ptr(dy), _ptr(dgamma), _ptr(dbeta), 1 if ws_zeroed else 0, _ptr(ws), _stream())
+        if ws_zeroed:
+            _lib.launch_count -= 1      # no memset node was enqueued
         dx = gemm_rows(dy, w2d).reshape(xshape) if ctx.needs_input_grad[0] else None   # dy.W^T: Bt = W as stored
         dw = gemm_wgrad(x2, dy) if ctx.needs_input_grad[1] else None
-        dbias = torch.zeros_like(gamma) if ctx.needs_input_grad[2] else None
+        dbias = _zeros(gamma.shape, torch.float32, gamma.device)[0] if ctx.needs_input_grad[2] else None
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None

@@ -32,6 +32,9 @@ class TrainStep:
         self.bucket = FlatGradBucket(self.store.parameters())
         # fused=True: one multi-tensor kernel per step (the foreach implementation is ~60 small kernels, 0.95 ms)
         self.opt = torch.optim.Adam(self.bucket.params, lr=lr, capturable=use_graph, fused=True)
+        # zero-initialised scratch of the dense glue, cleared once per step instead of ~100 separate fill nodes
+        from .. import _ops
+        self.arena = _ops.ZeroArena(self.device) if self.device.type == "cuda" else None
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None
@@ -48,9 +51,13 @@ class TrainStep:
             return pointasnl_sem_seg_res.get_loss(pred, self.labels, end_points, self.smpw)
 
     def _fwd_bwd(self):
+        from .. import _ops
         self.bucket.detach()
-        loss = self._forward()
-        loss.backward()
+        if self.arena is not None:
+            self.arena.reset()
+        with _ops.use_zero_arena(self.arena):
+            loss = self._forward()
+            loss.backward()
         self.bucket.pack()
         self.loss.copy_(loss.detach())
 

@@ -378,12 +378,12 @@ extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *g
 
 extern "C" int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *dout, const float *gamma,
                                 const float *beta, const float *mean, const float *var, float eps, int act, float *dy,
-                                float *dgamma, float *dbeta, void *workspace, void *stream) {
+                                float *dgamma, float *dbeta, int workspace_zeroed, void *workspace, void *stream) {
     PASNL_CHECK_ARG(rows >= 1 && c >= 1 && act >= 0 && act <= 2 && c <= 4096);
     PASNL_CHECK_ARG(y && dout && gamma && beta && mean && var && dy && dgamma && dbeta && workspace);
     cudaStream_t st = (cudaStream_t)stream;
     double *ws = (double *)workspace;
-    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st);
+    cudaError_t e = workspace_zeroed ? cudaSuccess : cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st);
     if (e != cudaSuccess) return (int)e;
     const Shape s = make_shape(c, aligned16(y) && aligned16(dout) && aligned16(dy));
     PASNL_CHECK_ARG(s.threads <= 1024);

@@ -1174,7 +1174,7 @@ gemm_wgrad_tm_kernel(long rows, long slab, int nstages, const float *__restrict_
 
 // dW[m][n] = X^T.Y with P = the operand that goes through TMEM (<= 128 columns per tile), Q = the transposed one
 inline int launch_wgrad_tm(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
-                           long ldw, cudaStream_t st) {
+                           long ldw, bool zeroed, cudaStream_t st) {
     // P: the wider operand if both fit in 128 columns (keeps the transposed operand and its smem traffic small);
     // otherwise whichever fits; if neither fits, Y in tiles of 128
     const bool p_is_y = (m <= kM && n <= kM) ? (n >= m) : (n <= kM ? true : (m <= kM ? false : true));
@@ -1195,7 +1195,7 @@ inline int launch_wgrad_tm(long rows, int m, int n, const float *X, long ldx, co
     slab = (slab + kRC - 1) / kRC * kRC;
     const long slabs = (rows + slab - 1) / slab;
     dim3 grid((unsigned)slabs, (unsigned)ptiles, (unsigned)qtiles);
-    cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
+    cudaError_t e = zeroed ? cudaSuccess : cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(gemm_wgrad_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1206,7 +1206,7 @@ inline int launch_wgrad_tm(long rows, int m, int n, const float *X, long ldx, co
 
 template <int NT>
 int launch_wgrad(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW, long ldw,
-                 cudaStream_t st) {
+                 bool zeroed, cudaStream_t st) {
     const bool vec = (ldx % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(Y) & 15u) == 0);
     const size_t smem = sizeof(float) * 2 * (size_t)(2 * kRC * kM + 2 * kRC * NT);
@@ -1219,7 +1219,7 @@ int launch_wgrad(long rows, int m, int n, const float *X, long ldx, const float 
     slab = (slab + kRC - 1) / kRC * kRC;
     const long slabs = (rows + slab - 1) / slab;
     dim3 grid((unsigned)slabs, (unsigned)mt, (unsigned)nt);
-    cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
+    cudaError_t e = zeroed ? cudaSuccess : cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
     if (e != cudaSuccess) return (int)e;
     if (vec) {
         auto kern = gemm_wgrad_kernel<NT, true>;
@@ -1305,7 +1305,7 @@ __global__ void __launch_bounds__(256) wgrad_narrow_kernel(long rows, long slab,
 }
 
 inline int launch_wgrad_narrow(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
-                               long ldw, cudaStream_t st) {
+                               long ldw, bool zeroed, cudaStream_t st) {
     const bool s_is_x = m <= n;                                   // the narrow operand
     const float *S = s_is_x ? X : Y, *Wd = s_is_x ? Y : X;
     const long lds = s_is_x ? ldx : ldy, ldwide = s_is_x ? ldy : ldx;
@@ -1319,7 +1319,7 @@ inline int launch_wgrad_narrow(long rows, int m, int n, const float *X, long ldx
     if (slab < 256) slab = 256;
     slab = (slab + 31) / 32 * 32;
     dim3 grid((unsigned)((rows + slab - 1) / slab), (unsigned)wtiles);
-    cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
+    cudaError_t e = zeroed ? cudaSuccess : cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
     if (e != cudaSuccess) return (int)e;
 #define PASNL_NARROW_WQ(MP, WQ) \
     wgrad_narrow_kernel<MP, WQ><<<grid, 256, 0, st>>>(rows, slab, S, lds, scols, Wd, ldwide, wcols, dW, os, ow, vec ? 1 : 0)
@@ -1362,23 +1362,24 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
 }
 
 extern "C" int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy,
-                                       float *dW, long ldw, void *stream) {
+                                       float *dW, long ldw, int dw_zeroed, void *stream) {
     PASNL_CHECK_ARG(rows >= 0 && m >= 1 && n >= 1 && ldx >= m && ldy >= n && ldw >= n);
     PASNL_CHECK_ARG(dW && (rows == 0 || (X && Y)) && ldw == n && m <= 128 * 65535 && n <= 256 * 65535);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool zeroed = dw_zeroed != 0;
     if (rows == 0) {
-        cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
+        cudaError_t e = zeroed ? cudaSuccess : cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)m * ldw, st);
         return (int)e;
     }
-    if ((m <= 16 || n <= 16) && rows >= 1024) return gtc::launch_wgrad_narrow(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
+    if ((m <= 16 || n <= 16) && rows >= 1024) return gtc::launch_wgrad_narrow(rows, m, n, X, ldx, Y, ldy, dW, ldw, zeroed, st);
     // long reductions: one warp-specialised CTA per SM with one operand fed through TMEM; short ones keep the
     // several-CTAs-per-SM kernel
     const int ntile = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
     const long tiles = (long)((m + gtc::kM - 1) / gtc::kM) * ((n + ntile - 1) / ntile);
     if (gtc::persist_enabled() && gtc::wgrad_tm_enabled() && rows * tiles >= 256L * gtc::sm_count()) {
-        return gtc::launch_wgrad_tm(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
+        return gtc::launch_wgrad_tm(rows, m, n, X, ldx, Y, ldy, dW, ldw, zeroed, st);
     }
-    if (n <= 32) return gtc::launch_wgrad<32>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
-    if (n <= 64) return gtc::launch_wgrad<64>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
-    return gtc::launch_wgrad<128>(rows, m, n, X, ldx, Y, ldy, dW, ldw, st);
+    if (n <= 32) return gtc::launch_wgrad<32>(rows, m, n, X, ldx, Y, ldy, dW, ldw, zeroed, st);
+    if (n <= 64) return gtc::launch_wgrad<64>(rows, m, n, X, ldx, Y, ldy, dW, ldw, zeroed, st);
+    return gtc::launch_wgrad<128>(rows, m, n, X, ldx, Y, ldy, dW, ldw, zeroed, st);
 }

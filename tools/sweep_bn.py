@@ -15,6 +15,6 @@ for rows, c in [(262144, 128), (524288, 64), (524288, 32), (16384, 128), (16384,
     ws = torch.empty(2 * c, device="cuda", dtype=torch.float64)
     def f():
         _ops._call("pasnl_bn_act_bwd", rows, c, _ops._ptr(y), _ops._ptr(dout), _ops._ptr(g), _ops._ptr(be), _ops._ptr(mean), _ops._ptr(var), 1e-3, 1,
-                   _ops._ptr(dy), _ops._ptr(dg), _ops._ptr(db), _ops._ptr(ws), _ops._stream())
+                   _ops._ptr(dy), _ops._ptr(dg), _ops._ptr(db), 0, _ops._ptr(ws), _ops._stream())
     med, best = timeit(f, iters=10)
     print(f"bn_act_bwd rows={rows} c={c}: {med:.1f} us ({20.0 * rows * c / med / 1e3:.0f} GB/s)", flush=True)
