@@ -239,7 +239,7 @@ class PointConvContract(torch.autograd.Function):
 
 def pointconv_contract(x, w):
     k, c = x.shape[-2], x.shape[-1]
-    if x.is_cuda and w.shape[-1] == 32 and k % 4 == 0 and c % 4 == 0 and k <= 256 and (k * c + k * 32 + 2 * c * 32) * 4 <= 200 * 1024:
+    if x.is_cuda and w.shape[-1] == 32 and k % 4 == 0 and c % 4 == 0 and k <= 256 and max(2 * (k * c + k * 32), k * c + k * 32 + 2 * c * 32) * 4 <= 200 * 1024:
         return PointConvContract.apply(x, w)
     return torch.matmul(x.transpose(-1, -2), w)
 
