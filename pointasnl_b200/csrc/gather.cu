@@ -219,6 +219,58 @@ __global__ void __launch_bounds__(kThreads) maxpool_k_grad_kernel(long gc, int k
     }
 }
 
+// Few groups with many neighbours (the global pooling of the classifier: 32 clouds x 512 points x 512 channels): one
+// thread per output would leave 16 K threads each walking 512 strided rows.  Here a CTA = 32 channels x 8 k-slices:
+// lanes read 128 contiguous bytes per row, the 8 slices are combined through shared memory.
+constexpr int kPoolSlices = 8;
+__global__ void __launch_bounds__(32 * kPoolSlices) maxpool_k_sliced_kernel(int k, int c, const float *__restrict__ x,
+                                                                          float *__restrict__ out) {
+    __shared__ float red[kPoolSlices][32];
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + lane;
+    const long g = blockIdx.y;
+    float m = -INFINITY;
+    if (ch < c) {
+        const float *p = x + g * (long)k * c + ch;
+#pragma unroll 4
+        for (int t = sl; t < k; t += kPoolSlices) m = fmaxf(m, __ldg(p + (long)t * c));
+    }
+    red[sl][lane] = m;
+    __syncthreads();
+    if (sl == 0 && ch < c) {
+#pragma unroll
+        for (int i = 1; i < kPoolSlices; ++i) m = fmaxf(m, red[i][lane]);
+        out[g * c + ch] = m;
+    }
+}
+__global__ void __launch_bounds__(32 * kPoolSlices) maxpool_k_grad_sliced_kernel(int k, int c, const float *__restrict__ x,
+                                                                               const float *__restrict__ out,
+                                                                               const float *__restrict__ grad_out,
+                                                                               float *__restrict__ grad_x) {
+    __shared__ int cnt_s[kPoolSlices][32];
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + lane;
+    const long g = blockIdx.y;
+    const bool ok = ch < c;
+    const float *p = x + g * (long)k * c + ch;
+    const float m = ok ? __ldg(out + g * c + ch) : 0.f;
+    int cnt = 0;
+    if (ok) {
+#pragma unroll 4
+        for (int t = sl; t < k; t += kPoolSlices) cnt += (__ldg(p + (long)t * c) == m) ? 1 : 0;
+    }
+    cnt_s[sl][lane] = cnt;
+    __syncthreads();
+    if (!ok) return;
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < kPoolSlices; ++i) total += cnt_s[i][lane];
+    const float share = __ldg(grad_out + g * c + ch) / (float)total;
+    float *q = grad_x + g * (long)k * c + ch;
+#pragma unroll 4
+    for (int t = sl; t < k; t += kPoolSlices) q[(long)t * c] = (__ldg(p + (long)t * c) == m) ? share : 0.f;
+}
+
 // ---------------------------------------------------------------- three_interpolate
 // out[row, :] = (p1*w1 + p2*w2) + p3*w3 with separate roundings (the x86 reference has no FMA): bit-exact.
 template <int VEC>
@@ -432,6 +484,11 @@ extern "C" int pasnl_maxpool_k(long groups, int k, int c, const float *x, float 
     PASNL_CHECK_ARG(groups >= 0 && k >= 1 && c >= 1);
     if (groups == 0) return PASNL_OK;
     PASNL_CHECK_ARG(x && out);
+    if (groups * c < (1L << 18) && k >= 8 * kPoolSlices && groups <= 65535) {
+        dim3 grid((unsigned)((c + 31) / 32), (unsigned)groups);
+        maxpool_k_sliced_kernel<<<grid, 32 * kPoolSlices, 0, (cudaStream_t)stream>>>(k, c, x, out);
+        return pasnl_launch_status();
+    }
     maxpool_k_kernel<<<grid_for(groups * c), kThreads, 0, (cudaStream_t)stream>>>(groups * c, k, c, x, out);
     return pasnl_launch_status();
 }
@@ -441,6 +498,11 @@ extern "C" int pasnl_maxpool_k_grad(long groups, int k, int c, const float *x, c
     PASNL_CHECK_ARG(groups >= 0 && k >= 1 && c >= 1);
     if (groups == 0) return PASNL_OK;
     PASNL_CHECK_ARG(x && out && grad_out && grad_x);
+    if (groups * c < (1L << 18) && k >= 8 * kPoolSlices && groups <= 65535) {
+        dim3 grid((unsigned)((c + 31) / 32), (unsigned)groups);
+        maxpool_k_grad_sliced_kernel<<<grid, 32 * kPoolSlices, 0, (cudaStream_t)stream>>>(k, c, x, out, grad_out, grad_x);
+        return pasnl_launch_status();
+    }
     maxpool_k_grad_kernel<<<grid_for(groups * c), kThreads, 0, (cudaStream_t)stream>>>(groups * c, k, c, x, out,
                                                                                         grad_out, grad_x);
     return pasnl_launch_status();

@@ -117,7 +117,7 @@ def test_tcgen05_wgrad_gemm(cuda, rows, m, n):
     assert err <= 5e-5 * scale + 1e-5, (err, scale)
 
 
-@pytest.mark.parametrize("shape", [(4, 128, 64, 134), (8, 512, 32, 9), (2, 1, 512, 131), (3, 7, 1, 5)])
+@pytest.mark.parametrize("shape", [(4, 128, 64, 134), (8, 512, 32, 9), (2, 1, 512, 131), (3, 7, 1, 5), (3, 1, 300, 70), (32, 512, 512)])
 def test_maxpool_over_neighbours_forward_backward_with_ties(cuda, shape):
     from pointasnl_b200 import _ops
     torch.manual_seed(sum(shape))
