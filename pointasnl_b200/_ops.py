@@ -552,9 +552,10 @@ def gemm_rows(a, bt, col_stats=None):
 
 class DenseBNAct(torch.autograd.Function):
     """act(batch_norm_train(x @ w + bias)) for a 1x1 conv / fully connected layer (tf_util.py:120-185,512-531).
-    The GEMMs are cuBLAS (torch.mm: plain library GEMMs); everything between them is fused pasnl kernels: forward
-    statistics (inside the GEMM epilogue when it can) and normalise+activate and two backward (reductions, apply).  The bias cancels inside train-mode batch
-    norm: it is not added and its gradient is exactly zero."""
+    Forward: y = x.W (gemm_rows: tcgen05 3xTF32 for the tall layers, whose epilogue also accumulates the batch-norm
+    statistics; cuBLAS for the small ones), then one normalise+activate kernel.  Backward: reductions, apply, the input
+    gradient (gemm_rows) and the weight gradient (gemm_wgrad).  The bias cancels inside train-mode batch norm: it is
+    not added and its gradient is exactly zero."""
 
     @staticmethod
     def forward(ctx, x, w2d, bias, gamma, beta, running_mean, running_var, decay, eps, act):

@@ -1,20 +1,30 @@
-// gemm_tc.cu -- fp32-accurate "rows" GEMM on tcgen05 tensor cores (3xTF32 split, TMEM accumulators), sm_100a.
+// gemm_tc.cu -- the fp32-accurate GEMMs of the 1x1-conv / fully-connected layers on tcgen05 tensor cores (3xTF32 split,
+// TMEM accumulators), sm_100a.  Two products:
 //
-//     C[rows, n] = A[rows, k] . Bt[n, k]^T          (A and Bt row-major: the contraction index is contiguous in both)
+//     rows GEMM     C[rows, n]  = A[rows, k] . Bt[n, k]^T     forward y = x.W (Bt = W^T), input gradient dx = dy.W^T
+//     weight grad   dW[m, n]    = sum_r X[r, m] * Y[r, n]
 //
-// This is the shape of every 1x1-conv / fully-connected layer around the point-set ops:
-// forward y = x.W (Bt = W^T), input gradient dx = dy.W^T (Bt = W).  rows = B*S*K is 10^4..10^6, k and n are 3..4096.
-// cuBLAS runs these as fp32 SIMT SGEMMs (~50 TFLOP/s, 5.5 ms of a 11.5 ms cls step); a single TF32 pass would break the
-// 1e-4 parity bar, so each product is split a = a_hi + a_lo (a_hi = a truncated to TF32) and accumulated as
-// a_hi.b_hi + a_hi.b_lo + a_lo.b_hi in fp32 TMEM (error ~2^-21 relative).  At 3 MMAs per k-step the tensor pipe still
-// outruns HBM for these skinny shapes, so the kernel is memory bound: bytes = 4*rows*(k+n).
+// rows = B*S*K is 10^4..10^6, k / n / m are 3..4096.  cuBLAS runs these as fp32 SIMT SGEMMs (~50 TFLOP/s, 5.5 ms of the
+// first 11.5 ms cls step); a single TF32 pass would break the 1e-4 parity bar, so each product is split a = a_hi + a_lo
+// (a_hi = a truncated to TF32) and accumulated as a_hi.b_hi + a_hi.b_lo + a_lo.b_hi in fp32 TMEM (~2^-21 relative).
 //
-// CTA = 256 threads = one 128-row x NT-column output tile; k is consumed in 16-wide chunks through TWO operand stages:
-//   all threads load + split the A (128 x 16) and Bt (NT x 16) chunks into the canonical no-swizzle K-major UMMA
-//   layout [row/8][k/4][row%8][4] (hi and lo copies); one thread issues 2 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=NT) and a
-//   tcgen05.commit to the stage's mbarrier; the MMAs run asynchronously while the CTA loads the next chunk into the
-//   other stage (a stage is rewritten only after its commit has arrived).  After the last chunk the accumulator rows
-//   leave TMEM through a shared-memory panel so that global stores are coalesced.
+// Kernels in this file, and when pasnl_gemm_*_tf32x3 picks them:
+//   gemm_rows_persist_kernel<NT>   rows >= 2*128*SMs, k <= 144, n <= 160: one CTA per SM, weights resident in shared
+//                                  memory, producer / MMA / epilogue warps over mbarriers, two TMEM accumulators
+//   gemm_rows_kernel<NT>           everything else: one 128 x NT tile per CTA, two operand stages (below)
+//   gemm_wgrad_tm_kernel           long reductions: one operand is fed through TMEM (tcgen05.st + TS-mode MMA)
+//   gemm_wgrad_kernel<NT>          short reductions: both operands transposed into shared memory, ~3 CTAs per SM
+//   wgrad_narrow_kernel<MP,WQ>     one operand with <= 16 columns: fp32 FMA streaming pass
+// What bounds them (ncu, profiles/r01b_*): the L1 / shared-memory data pipe -- operand STS plus the tensor core's own
+// shared-memory operand reads (3 MMAs per k-step re-read both operands) -- not HBM and not the tensor pipe.
+//
+// gemm_rows_kernel: CTA = 256 threads = one 128-row x NT-column output tile; k is consumed in 16-wide chunks through
+//   TWO operand stages: all threads load + split the A (128 x 16) and Bt (NT x 16) chunks into the canonical no-swizzle
+//   K-major UMMA layout [row/8][k/4][row%8][4] (hi and lo copies); one thread issues 2 k-steps x 3
+//   tcgen05.mma.kind::tf32 (M=128, N=NT) and a tcgen05.commit to the stage's mbarrier; the MMAs run asynchronously
+//   while the CTA loads the next chunk into the other stage (a stage is rewritten only after its commit has arrived).
+//   After the last chunk the accumulator rows leave TMEM through a shared-memory panel so that global stores are
+//   coalesced.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -98,18 +108,6 @@ __device__ __forceinline__ float4 load4(const float *__restrict__ base, long row
     }
     return x;
 }
-__device__ __forceinline__ void store_split4(float *hi, float *lo, int rows, int row, int kc, float4 x) {
-    // hi = x with the 13 low mantissa bits cleared (exactly a TF32 value), lo = x - hi (exact in fp32, |lo| < 2^-10 |x|).
-    // One LOP + one FADD per element: the F2F conversions (cvt.rna.tf32) run on the 16-lane XU pipe and were the
-    // bottleneck of the first revision.  The tensor core drops lo's bits below TF32: 2^-20 relative to x.
-    float4 h, l;
-    h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
-    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-    const int o = (kc * rows + row) * 4;
-    *reinterpret_cast<float4 *>(hi + o) = h;
-    *reinterpret_cast<float4 *>(lo + o) = l;
-}
-
 // Operand tile layout (canonical no-swizzle K-major, row-group major):  [row/8][kc = k/4][row%8][4 floats]
 //   core matrix = 8 rows x 16 bytes (128 contiguous bytes); LBO (next core matrix along k) = 128 bytes;
 //   SBO (next 8-row group) = (kKC/4) * 128 bytes.

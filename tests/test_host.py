@@ -143,3 +143,30 @@ def test_oracle_model_restatement_runs_and_has_the_reference_parameter_count():
     r2 = model_ref.Ref(None, dropout=False)
     model_ref.cls_forward(r2, torch.from_numpy(pc), torch.from_numpy(labels), adaptive_sample=True)
     assert "layer1/layer1/layer1/conv_kv_ds/weights" in r2.v      # the triple-nested scope of the reference
+
+
+def test_zero_arena_hands_out_disjoint_zeroed_slices_and_grows_on_reset():
+    """Host logic of the per-step zero arena used by the dense glue (pointasnl_b200/_ops.py: ZeroArena)."""
+    from pointasnl_b200 import _ops
+    arena = _ops.ZeroArena("cpu")
+    arena.reset()
+    assert arena.zeros((4, 3), torch.float32) is None            # nothing reserved yet: callers fall back to torch.zeros
+    assert arena.zeros((5,), torch.float64) is None
+    arena.reset()                                                # grows to the high-water mark of the previous step
+    a = arena.zeros((4, 3), torch.float32)
+    b = arena.zeros((5,), torch.float64)
+    assert a is not None and b is not None and a.shape == (4, 3) and b.dtype == torch.float64
+    assert float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0
+    a.fill_(1.0)
+    b.fill_(2.0)
+    assert float(a.sum()) == 12.0 and float(b.sum()) == 10.0     # disjoint storage
+    assert a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+    assert arena.zeros((1000,), torch.float32) is None           # over capacity: fall back, remembered for next reset
+    arena.reset()
+    c = arena.zeros((4, 3), torch.float32)
+    assert float(c.abs().sum()) == 0.0                           # cleared again
+    with _ops.use_zero_arena(arena):
+        t, from_arena = _ops._zeros((5,), torch.float64, "cpu")
+        assert from_arena and float(t.abs().sum()) == 0.0
+    t, from_arena = _ops._zeros((5,), torch.float64, "cpu")
+    assert not from_arena
