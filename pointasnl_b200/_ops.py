@@ -423,7 +423,8 @@ def gemm_wgrad(x, dy):
     # operands with a handful of columns (xyz: 3, 6, 9 channels) take the library's fp32 streaming kernel; 17..31
     # columns would be mostly padding in a 128-wide UMMA tile and stay on cuBLAS
     narrow = min(m, n) <= 16
-    if rows < 4096 or (m < 32 and not narrow) or (rows < 16384 and m >= 512) or not x.is_cuda or GEMM_IMPL != "tc":
+    # (tools/sweep_wgrad_small.py: with the TMEM-fed kernel tcgen05 wins from 2048 rows up, also for wide m)
+    if rows < 2048 or (m < 32 and not narrow) or not x.is_cuda or GEMM_IMPL != "tc":
         return torch.mm(x.t(), dy)
     if x.stride(1) != 1:
         x = x.contiguous()
