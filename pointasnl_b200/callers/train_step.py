@@ -30,8 +30,10 @@ class TrainStep:
         with torch.no_grad():   # materialise every variable (TF would do this at graph-construction time)
             self._forward()
         self.bucket = FlatGradBucket(self.store.parameters())
-        # fused=True: one multi-tensor kernel per step (the foreach implementation is ~60 small kernels, 0.95 ms)
-        self.opt = torch.optim.Adam(self.bucket.params, lr=lr, capturable=use_graph, fused=True)
+        # Adam over ONE flat parameter (all variables are views of it, its .grad is the gradient bucket): a single fused
+        # kernel per step (per-tensor multi-tensor launches: 0.12 ms; the foreach implementation: ~60 kernels, 0.95 ms)
+        self.flat_param = self.bucket.flatten_parameters()
+        self.opt = torch.optim.Adam([self.flat_param], lr=lr, capturable=use_graph, fused=True)
         # zero-initialised scratch of the dense glue, cleared once per step instead of ~100 separate fill nodes
         from .. import _ops
         self.arena = _ops.ZeroArena(self.device) if self.device.type == "cuda" else None

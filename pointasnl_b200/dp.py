@@ -78,6 +78,22 @@ class FlatGradBucket:
     def nbytes(self):
         return self.numel * 4
 
+    def flatten_parameters(self):
+        """Move every parameter's storage into ONE flat fp32 buffer (``p.data`` become views of it, values kept) and
+        return that buffer wrapped as a single Parameter whose ``.grad`` is the gradient bucket: the optimizer then
+        updates 1 tensor with 1 kernel instead of one multi-tensor launch chain over ~100 small tensors."""
+        flat = torch.empty(self.numel, device=self.flat.device, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = flat[off:off + n].view_as(p)
+                off += n
+        fp = torch.nn.Parameter(flat, requires_grad=True)
+        fp.grad = self.flat
+        return fp
+
 
 def shard_range(total, rank, world):
     """Rank r's slice [lo, hi) of `total` independent clouds (strong scaling); remainders go to the low ranks."""

@@ -170,3 +170,27 @@ def test_zero_arena_hands_out_disjoint_zeroed_slices_and_grows_on_reset():
         assert from_arena and float(t.abs().sum()) == 0.0
     t, from_arena = _ops._zeros((5,), torch.float64, "cpu")
     assert not from_arena
+
+
+def test_flat_parameter_adam_matches_per_tensor_adam():
+    """FlatGradBucket.flatten_parameters: one Adam over the flat buffer == Adam over the individual tensors."""
+    torch.manual_seed(3)
+    m1 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    m2 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    m2.load_state_dict(m1.state_dict())
+    x, y = torch.randn(16, 6), torch.randn(16, 3)
+    bucket = dp.FlatGradBucket(m1.parameters())
+    fp = bucket.flatten_parameters()
+    o1 = torch.optim.Adam([fp], lr=1e-2)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-2)
+    for _ in range(3):
+        bucket.detach()
+        ((m1(x) - y) ** 2).mean().backward()
+        bucket.pack()
+        assert fp.grad.data_ptr() == bucket.flat.data_ptr()
+        o1.step()
+        o2.zero_grad()
+        ((m2(x) - y) ** 2).mean().backward()
+        o2.step()
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
