@@ -155,6 +155,45 @@ __device__ __forceinline__ void load_tile_both(float *hi, float *lo, float *thi,
     }
 }
 
+// The same tile traffic split in two so that the global loads of the NEXT tile can be issued before the MMAs of the
+// current one are waited for: fetch (global -> registers) and store (registers -> split operand tiles).
+template <int ROWS, int D>
+struct TileRegs {
+    static constexpr int ITEMS = (ROWS / 8) * (D / 16);
+    static constexpr int PER_WARP = (ITEMS + kThreads / 32 - 1) / (kThreads / 32);
+    float4 v[PER_WARP];
+};
+template <int ROWS, int D>
+__device__ __forceinline__ void fetch_tile(TileRegs<ROWS, D> &tr, const float *__restrict__ src, long ld, int row0, int limit,
+                                           int warp, int lane) {
+    const int r8 = lane & 7, kq = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < TileRegs<ROWS, D>::PER_WARP; ++j) {
+        const int item = warp + (kThreads / 32) * j;
+        const int rg = item % (ROWS / 8), h = item / (ROWS / 8);
+        const int r = rg * 8 + r8, kc = kq + 4 * h;
+        tr.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < TileRegs<ROWS, D>::ITEMS && row0 + r < limit)
+            tr.v[j] = __ldg(reinterpret_cast<const float4 *>(src + (long)(row0 + r) * ld + kc * 4));
+    }
+}
+// natural tile (hi/lo, may be null) and/or transposed tile (thi/tlo, may be null)
+template <int ROWS, int D>
+__device__ __forceinline__ void store_tile(const TileRegs<ROWS, D> &tr, float *hi, float *lo, float *thi, float *tlo, int warp,
+                                           int lane) {
+    const int r8 = lane & 7, kq = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < TileRegs<ROWS, D>::PER_WARP; ++j) {
+        const int item = warp + (kThreads / 32) * j;
+        if (item < TileRegs<ROWS, D>::ITEMS) {
+            const int rg = item % (ROWS / 8), h = item / (ROWS / 8);
+            const int r = rg * 8 + r8, kc = kq + 4 * h;
+            if (hi != nullptr) store_split4(hi, lo, D / 4, r, kc, tr.v[j]);
+            if (thi != nullptr) store_split4_t(thi, tlo, ROWS / 4, r, kc, tr.v[j]);
+        }
+    }
+}
+
 constexpr int kFlushRows = 1024;   // contraction rows accumulated in TMEM before the partial is drained into registers
 
 // ------------------------------------------------------------------------------------------------ dQ (CTA = 128 queries)
@@ -217,10 +256,17 @@ __global__ void __launch_bounds__(kThreads) nl_bwd_dq_tc_kernel(int s, int n, in
     int in_group = 0;                                        // key tiles accumulated in TMEM since the last drain
     constexpr int kGroup = kFlushRows / BN;
 
+    TileRegs<BN, D> rk, rv;                                  // the next key tile, in flight while this one is processed
+    fetch_tile<BN, D>(rk, kvb, 2 * D, key_begin, key_end, warp, lane);
+    fetch_tile<BN, D>(rv, kvb + D, 2 * D, key_begin, key_end, warp, lane);
     for (int col0 = key_begin; col0 < key_end; col0 += BN) {
-        // ---- 1. Kf / V tiles: natural (B of S, dP) and Kf transposed (B of dQ)
-        load_tile_both<BN, D>(Khi, Klo, Kthi, Ktlo, kvb, 2 * D, col0, key_end, warp, lane);
-        load_tile<BN, D>(Vhi, Vlo, kvb + D, 2 * D, col0, key_end, warp, lane);
+        // ---- 1. Kf / V tiles: natural (B of S, dP) and Kf transposed (B of dQ); then request the next tile
+        store_tile<BN, D>(rk, Khi, Klo, Kthi, Ktlo, warp, lane);
+        store_tile<BN, D>(rv, Vhi, Vlo, nullptr, nullptr, warp, lane);
+        if (col0 + BN < key_end) {
+            fetch_tile<BN, D>(rk, kvb, 2 * D, col0 + BN, key_end, warp, lane);
+            fetch_tile<BN, D>(rv, kvb + D, 2 * D, col0 + BN, key_end, warp, lane);
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -343,14 +389,30 @@ __global__ void __launch_bounds__(kThreads) nl_bwd_dkv_tc_kernel(int s, int n, c
     int in_group = 0;
     constexpr int kGroup = kFlushRows / BQ;
 
+    TileRegs<BQ, D> rq, ro;                                  // the next query tile, in flight while this one is processed
+    fetch_tile<BQ, D>(rq, qb, D, 0, s, warp, lane);
+    fetch_tile<BQ, D>(ro, dob, D, 0, s, warp, lane);
+    float lse_n = 0.f, del_n = 0.f;
+    if (t < BQ && t < s) {
+        lse_n = __ldg(lse + (size_t)bi * s + t) * kLog2e;
+        del_n = __ldg(delta + (size_t)bi * s + t);
+    }
     for (int q0 = 0; q0 < s; q0 += BQ) {
-        // ---- 1. Q / dO tiles, natural and transposed; per-query lse and delta
-        load_tile_both<BQ, D>(Qhi, Qlo, Qthi, Qtlo, qb, D, q0, s, warp, lane);
-        load_tile_both<BQ, D>(Ohi, Olo, Othi, Otlo, dob, D, q0, s, warp, lane);
+        // ---- 1. Q / dO tiles, natural and transposed; per-query lse and delta; then request the next tile
+        store_tile<BQ, D>(rq, Qhi, Qlo, Qthi, Qtlo, warp, lane);
+        store_tile<BQ, D>(ro, Ohi, Olo, Othi, Otlo, warp, lane);
         if (t < BQ) {
-            const bool ok = q0 + t < s;
-            lse_c[t] = ok ? __ldg(lse + (size_t)bi * s + q0 + t) * kLog2e : 0.f;
-            del_c[t] = ok ? __ldg(delta + (size_t)bi * s + q0 + t) : 0.f;
+            lse_c[t] = lse_n;
+            del_c[t] = del_n;
+        }
+        if (q0 + BQ < s) {
+            fetch_tile<BQ, D>(rq, qb, D, q0 + BQ, s, warp, lane);
+            fetch_tile<BQ, D>(ro, dob, D, q0 + BQ, s, warp, lane);
+            if (t < BQ) {
+                const bool ok = q0 + BQ + t < s;
+                lse_n = ok ? __ldg(lse + (size_t)bi * s + q0 + BQ + t) * kLog2e : 0.f;
+                del_n = ok ? __ldg(delta + (size_t)bi * s + q0 + BQ + t) : 0.f;
+            }
         }
         fence_async_smem();
         tc_fence_before();
