@@ -551,6 +551,14 @@ def gemm_rows(a, bt, col_stats=None):
     return out if col_stats is None else (out, fuse_stats)
 
 
+def _bn_single_launch(rows, c):
+    """Mirror of dense_glue.cu's choice: small layers run clear + reduce + apply as ONE cooperative launch."""
+    if _os.environ.get("PASNL_BN_COOP", "1")[:1] == "0":
+        return False
+    lanes = c // 4 if c % 4 == 0 else c
+    return rows * c <= (4 << 20) and lanes <= 256
+
+
 class DenseBNAct(torch.autograd.Function):
     """act(batch_norm_train(x @ w + bias)) for a 1x1 conv / fully connected layer (tf_util.py:120-185,512-531).
     Forward: y = x.W (gemm_rows: tcgen05 3xTF32 for the tall layers, whose epilogue also accumulates the batch-norm
@@ -574,8 +582,8 @@ class DenseBNAct(torch.autograd.Function):
         _call("pasnl_bn_act_fwd", rows, cout, _ptr(y), _ptr(gamma), _ptr(beta), float(eps), int(act), _ptr(out),
               _ptr(mean), _ptr(var), _ptr(bias), _ptr(running_mean), _ptr(running_var), float(decay),
               1 if stats_ready else 0, _ptr(ws), _stream())
-        if stats_ready:
-            _lib.launch_count -= 2      # no memset / statistics kernels were enqueued by that call
+        if stats_ready or _bn_single_launch(rows, cout):
+            _lib.launch_count -= 2      # no memset / statistics nodes (fused in the GEMM, or one cooperative launch)
         ctx.save_for_backward(x2, w2d, y, gamma, beta, mean, var)
         ctx.meta = (float(eps), int(act), x.shape)
         return out.reshape(x.shape[:-1] + (cout,))
@@ -597,7 +605,9 @@ class DenseBNAct(torch.autograd.Function):
             ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
         _call("pasnl_bn_act_bwd", rows, cout, _ptr(y), _ptr(dout), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), eps,
               act, _ptr(dy), _ptr(dgamma), _ptr(dbeta), 1 if ws_zeroed else 0, _ptr(ws), _stream())
-        if ws_zeroed:
+        if _bn_single_launch(rows, cout):
+            _lib.launch_count -= 2      # clear + reduce + apply ran as one cooperative launch
+        elif ws_zeroed:
             _lib.launch_count -= 1      # no memset node was enqueued
         dx = gemm_rows(dy, w2d).reshape(xshape) if ctx.needs_input_grad[0] else None   # dy.W^T: Bt = W as stored
         dw = gemm_wgrad(x2, dy) if ctx.needs_input_grad[1] else None

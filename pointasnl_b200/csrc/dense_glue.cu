@@ -12,9 +12,12 @@
 //   stats 4*rows*c bytes; apply 8*rows*c; bwd reduce 8*rows*c; bwd apply 12*rows*c.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 using namespace pasnl;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -47,12 +50,13 @@ __device__ __forceinline__ float act_grad(float z, int act) {
     return 1.f;
 }
 
+extern __shared__ float red[];   // [2][threads][VEC] partial sums of the reduction phases
+
 // ---------------------------------------------------------------- forward statistics
 // ws[0..c) += sum(y - shift), ws[c..2c) += sum((y - shift)^2), shift = y[0, :]
 template <int VEC>
-__global__ void bn_stats_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
+__device__ __forceinline__ void bn_stats_body(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                 double *__restrict__ ws) {
-    extern __shared__ float red[];   // [2][threads][VEC]
     const int t = threadIdx.x, cv = t % cvec, ry = t / cvec;
     const int col = cv * VEC;
     float shift[VEC], s1[VEC], s2[VEC];
@@ -119,7 +123,7 @@ __global__ void bn_stats_kernel(long rows, int c, int cvec, int rpb, const float
 // derives its channels' mean and variance from the fp64 sums, CTA 0 also publishes them (saved for the backward) and
 // updates the moving averages -- one launch less per layer.
 template <int VEC>
-__global__ void bn_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
+__device__ __forceinline__ void bn_apply_body(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                 const double *__restrict__ ws, int shifted, float *__restrict__ mean,
                                 float *__restrict__ var, const float *__restrict__ bias, float *__restrict__ running_mean,
                                 float *__restrict__ running_var, float decay, const float *__restrict__ gamma,
@@ -182,11 +186,10 @@ __global__ void bn_apply_kernel(long rows, int c, int cvec, int rpb, const float
 // ---------------------------------------------------------------- backward
 // ws[0..c) += sum dz, ws[c..2c) += sum dz*xhat,  dz = dout * act'(z), z recomputed exactly as in the forward
 template <int VEC>
-__global__ void bn_bwd_reduce_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
+__device__ __forceinline__ void bn_bwd_reduce_body(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                      const float *__restrict__ dout, const float *__restrict__ mean,
                                      const float *__restrict__ var, const float *__restrict__ gamma,
                                      const float *__restrict__ beta, float eps, int act, double *__restrict__ ws) {
-    extern __shared__ float red[];
     const int t = threadIdx.x, cv = t % cvec, ry = t / cvec;
     const int col = cv * VEC;
     float mu[VEC], rstd[VEC], sc[VEC], be[VEC], s1[VEC], s2[VEC];
@@ -255,7 +258,7 @@ __global__ void bn_bwd_reduce_kernel(long rows, int c, int cvec, int rpb, const 
 
 // dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz*xhat)); block 0 also emits dgamma / dbeta
 template <int VEC>
-__global__ void bn_bwd_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
+__device__ __forceinline__ void bn_bwd_apply_body(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                     const float *__restrict__ dout, const float *__restrict__ mean,
                                     const float *__restrict__ var, const float *__restrict__ gamma,
                                     const float *__restrict__ beta, float eps, int act,
@@ -320,6 +323,84 @@ __global__ void bn_bwd_apply_kernel(long rows, int c, int cvec, int rpb, const f
     }
 }
 
+// ---------------------------------------------------------------- kernels
+template <int VEC>
+__global__ void bn_stats_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y, double *__restrict__ ws) {
+    bn_stats_body<VEC>(rows, c, cvec, rpb, y, ws);
+}
+template <int VEC>
+__global__ void bn_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
+                                const double *__restrict__ ws, int shifted, float *__restrict__ mean,
+                                float *__restrict__ var, const float *__restrict__ bias, float *__restrict__ running_mean,
+                                float *__restrict__ running_var, float decay, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, float eps, int act, float *__restrict__ out) {
+    bn_apply_body<VEC>(rows, c, cvec, rpb, y, ws, shifted, mean, var, bias, running_mean, running_var, decay, gamma, beta,
+                       eps, act, out);
+}
+template <int VEC>
+__global__ void bn_bwd_reduce_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
+                                     const float *__restrict__ dout, const float *__restrict__ mean,
+                                     const float *__restrict__ var, const float *__restrict__ gamma,
+                                     const float *__restrict__ beta, float eps, int act, double *__restrict__ ws) {
+    bn_bwd_reduce_body<VEC>(rows, c, cvec, rpb, y, dout, mean, var, gamma, beta, eps, act, ws);
+}
+template <int VEC>
+__global__ void bn_bwd_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
+                                    const float *__restrict__ dout, const float *__restrict__ mean,
+                                    const float *__restrict__ var, const float *__restrict__ gamma,
+                                    const float *__restrict__ beta, float eps, int act,
+                                    const double *__restrict__ ws, float *__restrict__ dy,
+                                    float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    bn_bwd_apply_body<VEC>(rows, c, cvec, rpb, y, dout, mean, var, gamma, beta, eps, act, ws, dy, dgamma, dbeta);
+}
+
+// Small layers (a few MB): the three dependent launches (clear, reduce, apply) cost more than the data movement, so the
+// phases run inside ONE cooperative launch of at most one CTA per SM, separated by grid barriers; the second pass
+// re-reads the CTA's own rows from L2.
+template <int VEC>
+__global__ void __launch_bounds__(kMaxThreads) bn_fwd_coop_kernel(
+    long rows, int c, int cvec, int rpb, const float *__restrict__ y, double *ws, float *__restrict__ mean,
+    float *__restrict__ var, const float *__restrict__ bias, float *__restrict__ running_mean,
+    float *__restrict__ running_var, float decay, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+    int act, float *__restrict__ out) {
+    cg::grid_group grid = cg::this_grid();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * c; i += gridDim.x * blockDim.x) ws[i] = 0.0;
+    grid.sync();
+    bn_stats_body<VEC>(rows, c, cvec, rpb, y, ws);
+    grid.sync();
+    bn_apply_body<VEC>(rows, c, cvec, rpb, y, ws, 1, mean, var, bias, running_mean, running_var, decay, gamma, beta, eps,
+                       act, out);
+}
+template <int VEC>
+__global__ void __launch_bounds__(kMaxThreads) bn_bwd_coop_kernel(
+    long rows, int c, int cvec, int rpb, const float *__restrict__ y, const float *__restrict__ dout,
+    const float *__restrict__ mean, const float *__restrict__ var, const float *__restrict__ gamma,
+    const float *__restrict__ beta, float eps, int act, double *ws, float *__restrict__ dy, float *__restrict__ dgamma,
+    float *__restrict__ dbeta) {
+    cg::grid_group grid = cg::this_grid();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * c; i += gridDim.x * blockDim.x) ws[i] = 0.0;
+    grid.sync();
+    bn_bwd_reduce_body<VEC>(rows, c, cvec, rpb, y, dout, mean, var, gamma, beta, eps, act, ws);
+    grid.sync();
+    bn_bwd_apply_body<VEC>(rows, c, cvec, rpb, y, dout, mean, var, gamma, beta, eps, act, ws, dy, dgamma, dbeta);
+}
+
+// layers up to this many elements take the single cooperative launch (PASNL_BN_COOP=0 disables it)
+constexpr long kCoopMaxElems = 4L << 20;
+bool coop_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("PASNL_BN_COOP");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+int coop_grid(long rows, int rpb) {
+    long blocks = (rows + (long)rpb * 8 - 1) / ((long)rpb * 8);
+    if (blocks > 148) blocks = 148;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
 bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 int stream_grid(long work, int threads) {
@@ -355,13 +436,25 @@ extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *g
     PASNL_CHECK_ARG(y && gamma && beta && out && mean && var && workspace);
     cudaStream_t st = (cudaStream_t)stream;
     double *ws = (double *)workspace;
+    const Shape s = make_shape(c, aligned16(y) && aligned16(out));
+    PASNL_CHECK_ARG(s.threads <= 1024);
+    const size_t smem = sizeof(float) * 2 * (size_t)s.threads * s.vec;
+    if (!stats_ready && coop_enabled() && rows * c <= kCoopMaxElems && s.threads <= kMaxThreads) {
+        // small layer, statistics not provided: clear + statistics + normalise/activate in one cooperative launch
+        long rows_ = rows;
+        int c_ = c, cvec_ = s.cvec, rpb_ = s.rpb, act_ = act;
+        float eps_ = eps, decay_ = decay;
+        void *args[] = {&rows_, &c_, &cvec_, &rpb_, (void *)&y, &ws, &mean, &var, (void *)&bias, &running_mean,
+                        &running_var, &decay_, (void *)&gamma, (void *)&beta, &eps_, &act_, &out};
+        const void *fn = s.vec == 4 ? (const void *)bn_fwd_coop_kernel<4> : (const void *)bn_fwd_coop_kernel<1>;
+        cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(coop_grid(rows, s.rpb)), dim3(s.threads), args, smem, st);
+        if (ce != cudaSuccess) return (int)ce;
+        return pasnl_launch_status();
+    }
     if (!stats_ready) {
         cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st);
         if (e != cudaSuccess) return (int)e;
     }
-    const Shape s = make_shape(c, aligned16(y) && aligned16(out));
-    PASNL_CHECK_ARG(s.threads <= 1024);
-    const size_t smem = sizeof(float) * 2 * (size_t)s.threads * s.vec;
     const int rg = reduce_grid(rows, s.rpb);
     const int ag = apply_grid(rows, s.rpb);
     if (s.vec == 4) {
@@ -383,11 +476,22 @@ extern "C" int pasnl_bn_act_bwd(long rows, int c, const float *y, const float *d
     PASNL_CHECK_ARG(y && dout && gamma && beta && mean && var && dy && dgamma && dbeta && workspace);
     cudaStream_t st = (cudaStream_t)stream;
     double *ws = (double *)workspace;
-    cudaError_t e = workspace_zeroed ? cudaSuccess : cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st);
-    if (e != cudaSuccess) return (int)e;
     const Shape s = make_shape(c, aligned16(y) && aligned16(dout) && aligned16(dy));
     PASNL_CHECK_ARG(s.threads <= 1024);
     const size_t smem = sizeof(float) * 2 * (size_t)s.threads * s.vec;
+    if (coop_enabled() && rows * c <= kCoopMaxElems && s.threads <= kMaxThreads) {
+        long rows_ = rows;
+        int c_ = c, cvec_ = s.cvec, rpb_ = s.rpb, act_ = act;
+        float eps_ = eps;
+        void *args[] = {&rows_, &c_, &cvec_, &rpb_, (void *)&y, (void *)&dout, (void *)&mean, (void *)&var, (void *)&gamma,
+                        (void *)&beta, &eps_, &act_, &ws, &dy, &dgamma, &dbeta};
+        const void *fn = s.vec == 4 ? (const void *)bn_bwd_coop_kernel<4> : (const void *)bn_bwd_coop_kernel<1>;
+        cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(coop_grid(rows, s.rpb)), dim3(s.threads), args, smem, st);
+        if (ce != cudaSuccess) return (int)ce;
+        return pasnl_launch_status();
+    }
+    cudaError_t e = workspace_zeroed ? cudaSuccess : cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st);
+    if (e != cudaSuccess) return (int)e;
     const int rg = reduce_grid(rows, s.rpb);
     const int ag = apply_grid(rows, s.rpb);
     if (s.vec == 4) {
