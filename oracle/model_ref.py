@@ -1,5 +1,8 @@
 """Layer- and model-level CPU restatement of the reference's TF graph code (TEST INFRASTRUCTURE, see
-oracle/__init__.py; **parity unpinned** -- TensorFlow cannot run here).
+oracle/__init__.py).  **Pinned**: tests/test_oracle.py checks every function here against
+tests/golden/tf_graph_*.npz, which were produced by executing the reference's own Python files (imported unmodified
+from /root/reference) on the stand-in tensorflow module tests/golden/tf_shim.py -- outputs to 1e-9, gradient digests of
+every variable to 1e-7, fp64.
 
 It follows utils/pointasnl_util.py, utils/pointnet_util.py, utils/tf_util.py and the two model files line by line,
 in the reference's own (unfused) formulation: gather_nd-style indexing, materialised attention maps, separate
@@ -84,10 +87,14 @@ def gather_nd(t, idx):
 class Ref:
     """Holds the variables (TF name -> tensor) and evaluation switches."""
 
-    def __init__(self, variables=None, dtype=torch.float32, dropout=True, native_knn=True, native_interp=False, seed=0):
-        """variables: TF name -> tensor (e.g. the product's store.variables()), or None to create them lazily with the
-        reference's initialisers (xavier-uniform weights, zero biases, BN gamma 1 / beta 0) -- used by the CPU baseline."""
+    def __init__(self, variables=None, dtype=torch.float32, dropout=True, native_knn=True, native_interp=False, seed=0,
+                 init="tf"):
+        """variables: TF name -> tensor (e.g. the product's store.variables()), or None to create them lazily: init="tf"
+        = the reference's initialisers (xavier-uniform weights, zero biases, BN gamma 1 / beta 0; used by the CPU
+        baseline), init="golden" = oracle.golden_init.golden_init(name, shape, kind), the name-seeded values the
+        tests/golden/tf_graph_*.npz vectors were generated with."""
         self.lazy = variables is None
+        self.init = init
         self.v = {} if self.lazy else {
             k: v.detach().cpu().to(dtype).requires_grad_(v.dtype.is_floating_point and "moving_" not in k)
             for k, v in variables.items()}
@@ -103,7 +110,10 @@ class Ref:
         if full not in self.v:
             if not self.lazy:
                 raise KeyError(full)
-            if kind == "xavier":      # tf.contrib.layers.xavier_initializer (uniform), tf_util.py:_variable_with_weight_decay
+            if self.init == "golden":
+                from .golden_init import golden_init
+                t = torch.from_numpy(golden_init(full, shape, name))
+            elif kind == "xavier":      # tf.contrib.layers.xavier_initializer (uniform), tf_util.py:_variable_with_weight_decay
                 fan_in = int(np.prod(shape[:-1]))
                 fan_out = int(np.prod(shape[:-2])) * shape[-1] if len(shape) > 2 else shape[-1]
                 limit = math.sqrt(6.0 / (fan_in + fan_out))
@@ -278,6 +288,26 @@ def get_repulsion_loss(r, pred, nsample=20, radius=0.07):
     return torch.mean(radius - dist * weight)
 
 
+def decoding_layer(r, xyz1, xyz2, points1, points2, nsample, mlp, scope, bn=True):
+    """PointASNLDecodingLayer (:294-351), NL=False (the default every caller uses)"""
+    with r.vs(scope):
+        dist, idx = three_nn(xyz1, xyz2)
+        dist = torch.clamp(dist, min=1e-10)
+        norm = (1.0 / dist).sum(dim=2, keepdim=True)
+        weight = (1.0 / dist) / norm
+        interpolated = three_interpolate(points2, idx, weight, r.native_interp)
+        grouped_xyz, grouped_feature, _ = grouping(r, interpolated, nsample, xyz1, xyz1)
+        grouped_xyz = grouped_xyz - xyz1.unsqueeze(2)
+        with r.vs("decode_weight_net"):
+            w = r.dense(grouped_xyz, "wconv0", 32, bn=True)
+        new_points = torch.matmul(grouped_feature.transpose(2, 3), w)
+        new_points = r.dense(new_points, "decode_after_conv", mlp[0], bn=bn, full_width=True)
+        new_points1 = torch.cat([new_points, points1.unsqueeze(2)], dim=-1) if points1 is not None else new_points
+        for i in range(1, len(mlp)):
+            new_points1 = r.dense(new_points1, "conv_%d" % i, mlp[i], bn=bn)
+        return new_points1.squeeze(2)
+
+
 # ---------------------------------------------------------------------------------------------- pointnet_util.py
 def sa_group_all(r, xyz, points, mlp, scope):
     """pointnet_sa_module(group_all=True) (pointnet_util.py:85-150 with :57-82)"""
@@ -369,5 +399,9 @@ def seg_forward(r, point_cloud, num_class, label=None, smpw=None, feature_channe
     w = smpw.reshape(-1).to(r.dtype)
     classify_loss = (ce * w).sum() / torch.count_nonzero(w).clamp(min=1)
     uniform_loss = get_repulsion_loss(r, l1_xyz, 20, radius)
-    total = classify_loss + uniform_weight * uniform_loss + 1e-4 * l2_on_weights(r)
+    # :83 `weight_reg = tf.add_n(tf.get_collection('losses'))`: tf.losses.sparse_softmax_cross_entropy registers its
+    # result in the 'losses' collection (GraphKeys.LOSSES), and no weight-decay term is ever added to it (every
+    # training script leaves weight_decay=None) -> weight_reg IS classify_loss: it is counted twice (:85).
+    weight_reg = classify_loss
+    total = classify_loss + weight_reg + uniform_weight * uniform_loss + 1e-4 * l2_on_weights(r)
     return net, total

@@ -1,8 +1,8 @@
 """torch-facing wrappers of the C ABI: argument validation, output allocation, autograd.
 
 PyTorch is used here for device memory, streams and autograd plumbing only; every computation below is one
-``pasnl_*`` call into libpasnl_b200.so (include/pasnl.h).  No op has a CPU or pure-PyTorch fallback: a non-CUDA
-tensor is an error.
+``pasnl_*`` call into libpasnl_b200.so (include/pasnl.h).  No hot-path op (sections "sampling" ... "Non-Local core")
+has a CPU or pure-PyTorch fallback: a non-CUDA tensor is an error.
 
 Gradient contract = the reference's registrations: gather_point -> inp (tf_sampling.py:43-47),
 group_point -> points (tf_grouping.py:42-46), three_interpolate -> points only (tf_interpolate.py:29-34); no
@@ -21,6 +21,14 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_current_device(t, name):
+    """Kernels are launched on the CURRENT device's current stream with raw pointers: a tensor living on another
+    device would be dereferenced on the wrong GPU (illegal address at best).  Fail loudly instead."""
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise ValueError(f"{name} is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         "wrap the call in `with torch.cuda.device(tensor.device):`")
+
+
 def _f32(t, name):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
@@ -28,6 +36,7 @@ def _f32(t, name):
         raise ValueError(f"{name} must be a CUDA tensor: pointasnl_b200 has no CPU path (got device {t.device})")
     if t.dtype != torch.float32:
         raise ValueError(f"{name} must be float32, got {t.dtype}")
+    _on_current_device(t, name)
     return t.contiguous()
 
 
@@ -41,6 +50,7 @@ def _i32(t, name):
             t = t.to(torch.int32)
         else:
             raise ValueError(f"{name} must be an integer tensor, got {t.dtype}")
+    _on_current_device(t, name)
     return t.contiguous()
 
 

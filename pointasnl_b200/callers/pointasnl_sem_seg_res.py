@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import tf_util
-from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss
+from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss, index_cache
 from ..pointnet_util import pointnet_fp_module
 from .pointasnl_cls import l2_on_weights
 
@@ -23,6 +23,11 @@ def _sa(xyz, feat, npoint, mlp, scope, k_as, nl, cfg):
 
 def get_model(point_cloud, is_training, num_class, bn_decay=None, weight_decay=None, feature_channel=0):
     """point_cloud (B, N, 3+feature_channel) -> per-point logits (B, N, num_class), end_points."""
+    with index_cache():      # layer1_1 / layer1_2 repeat FPS + kNN on identical inputs (:35-36): computed once
+        return _get_model(point_cloud, is_training, num_class, bn_decay, weight_decay, feature_channel)
+
+
+def _get_model(point_cloud, is_training, num_class, bn_decay, weight_decay, feature_channel):
     end_points = {}
     num_point = point_cloud.shape[1]
     if feature_channel > 0:
@@ -76,5 +81,11 @@ def get_loss(pred, label, end_points, smpw=1.0, uniform_weight=0.01, weights_dec
     else:
         classify_loss = (ce * smpw).mean()
     uniform_loss = get_repulsion_loss(end_points["l1_xyz"], nsample=20, radius=radius)
-    weight_reg = store.regularization_loss()      # tf.add_n(tf.get_collection('losses'))
+    # :83 `weight_reg = tf.add_n(tf.get_collection('losses'))`.  tf.losses.sparse_softmax_cross_entropy registers its
+    # result in that very collection (loss_collection=GraphKeys.LOSSES), next to the per-variable weight-decay terms
+    # of tf_util._variable_with_weight_decay: weight_reg = classify_loss + sum(wd * l2_loss(var)), so the total (:85)
+    # counts the classification loss TWICE.  (Every reference training script leaves weight_decay=None; without the
+    # registered classify_loss `tf.add_n([])` would not even build.)  Reproduced, and pinned by
+    # tests/golden/tf_graph_seg.npz, which executes the reference's own get_loss.
+    weight_reg = classify_loss + store.regularization_loss()
     return classify_loss + weight_reg + uniform_weight * uniform_loss + regularization_loss

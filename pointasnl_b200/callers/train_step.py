@@ -9,12 +9,16 @@ from . import pointasnl_cls, pointasnl_sem_seg_res
 
 class TrainStep:
     def __init__(self, model="cls", batch_size=32, num_point=1024, device="cuda", adaptive_sample=False,
-                 num_class=None, feature_channel=3, lr=1e-3, seed=0, use_graph=False):
+                 num_class=None, feature_channel=3, lr=1e-3, seed=0, use_graph=False, radius=0.07):
+        """model: 'cls' (models/pointasnl_cls.py) or 'seg' (models/pointasnl_sem_seg_res.py; feature_channel=3, radius=0.07
+        is the ScanNet configuration, feature_channel=1, num_class=20, radius=0.2 the SemanticKITTI one,
+        SemanticKITTI/train_semantic_kitti.py:81, train_semantic_kitti_grid.py:144)."""
         self.kind = model
         self.device = torch.device(device)
         self.batch_size, self.num_point = batch_size, num_point
         self.adaptive_sample = adaptive_sample
         self.feature_channel = feature_channel
+        self.radius = radius
         self.num_class = num_class or (40 if model == "cls" else 21)
         self.store = tf_util.VariableStore(self.device, seed=seed)
         c = 6 if model == "cls" else 3 + feature_channel
@@ -27,8 +31,10 @@ class TrainStep:
             self.labels = torch.zeros((batch_size, num_point), dtype=torch.int64, device=self.device)
             self.smpw = torch.ones((batch_size, num_point), device=self.device)
         self.loss = torch.zeros((), device=self.device)
-        with torch.no_grad():   # materialise every variable (TF would do this at graph-construction time)
-            self._forward()
+        # materialise every variable (TF does this at graph-construction time) with an inference-mode pass: it creates
+        # the same variables but neither updates the moving averages nor draws dropout masks
+        with torch.no_grad():
+            self._forward(is_training=False)
         self.bucket = FlatGradBucket(self.store.parameters())
         # Adam over ONE flat parameter (all variables are views of it, its .grad is the gradient bucket): a single fused
         # kernel per step (per-tensor multi-tensor launches: 0.12 ms; the foreach implementation: ~60 kernels, 0.95 ms)
@@ -41,16 +47,16 @@ class TrainStep:
         self.use_graph = use_graph
         self.launches_per_step = None
 
-    def _forward(self):
+    def _forward(self, is_training=True):
         with self.store.as_default():
             if self.kind == "cls":
-                pred, end_points = pointasnl_cls.get_model(self.points, True, use_normal=True,
+                pred, end_points = pointasnl_cls.get_model(self.points, is_training, use_normal=True,
                                                            adaptive_sample=self.adaptive_sample,
                                                            num_class=self.num_class)
                 return pointasnl_cls.get_loss(pred, self.labels, end_points)
-            pred, end_points = pointasnl_sem_seg_res.get_model(self.points, True, self.num_class,
+            pred, end_points = pointasnl_sem_seg_res.get_model(self.points, is_training, self.num_class,
                                                                feature_channel=self.feature_channel)
-            return pointasnl_sem_seg_res.get_loss(pred, self.labels, end_points, self.smpw)
+            return pointasnl_sem_seg_res.get_loss(pred, self.labels, end_points, self.smpw, radius=self.radius)
 
     def _fwd_bwd(self):
         from .. import _ops

@@ -4,10 +4,9 @@ scope) are kept; variables live in the active ``tf_util.VariableStore`` under th
 
 What runs where: every point-set step (FPS, kNN / ball query, neighbourhood gathers, the Adaptive-Sampling
 attention + re-sampling, the Non-Local attention) is one ``pasnl_*`` CUDA kernel (include/pasnl.h); the 1x1-conv /
-BN / ReLU glue between them is PyTorch (cuBLAS), see tf_util.py.
+BN / ReLU glue between them runs on the library's tcgen05 GEMMs and fused batch-norm kernels (tf_util.py, _ops.py).
 """
 import math
-import weakref
 
 import torch
 
@@ -17,21 +16,37 @@ from .tf_interpolate import three_interpolate, three_nn  # noqa: F401  (re-expor
 
 # ---------------------------------------------------------------------------------------------- memoisation
 # FPS and the neighbour searches are pure functions of coordinates.  pointasnl_sem_seg_res runs layer1_1 and
-# layer1_2 on the very same inputs (reference models/pointasnl_sem_seg_res.py:35-36: FPS 10240->1280 and kNN twice),
-# so results are memoised per source TENSOR OBJECT (weak reference + version counter: an in-place edit or a new
-# tensor at a recycled address can never alias a stale entry).
-_memo = {}
+# layer1_2 on the very same inputs (reference models/pointasnl_sem_seg_res.py:35-36: FPS 10240->1280 and kNN twice).
+# The INTEGER index results (never an autograd-tracked tensor) are memoised per source tensor object, and only inside
+# an explicit ``index_cache()`` scope that a caller opens around ONE forward pass (callers/pointasnl_sem_seg_res.py):
+# outside a scope nothing is cached, so static input buffers, CUDA-graph capture after warm-up steps and grad-mode
+# changes can never see a stale entry.
+_memo = None
+
+
+class index_cache:
+    """``with index_cache(): model forward`` -- FPS / neighbour indices computed twice on the same tensors are reused
+    within the block and dropped at its end."""
+
+    def __enter__(self):
+        global _memo
+        self.prev, _memo = _memo, {}
+        return self
+
+    def __exit__(self, *exc):
+        global _memo
+        _memo = self.prev
 
 
 def _memoized(tag, srcs, extra, fn):
-    key = (tag, tuple(id(t) for t in srcs), extra)
+    if _memo is None:
+        return fn()
+    key = (tag, tuple(id(t) for t in srcs), tuple(t._version for t in srcs), extra)
     hit = _memo.get(key)
-    if hit is not None and all(r() is t and v == t._version for r, v, t in zip(hit[0], hit[1], srcs)):
-        return hit[2]
+    if hit is not None and all(h is t for h, t in zip(hit[0], srcs)):
+        return hit[1]
     res = fn()
-    if len(_memo) >= 16:
-        _memo.clear()
-    _memo[key] = ([weakref.ref(t) for t in srcs], [t._version for t in srcs], res)
+    _memo[key] = (tuple(srcs), res)     # strong refs: an id cannot be recycled while the scope is open
     return res
 
 
@@ -43,24 +58,28 @@ def knn_query(k, support_pts, query_pts):
     return _ops.knn(k, support_pts, query_pts)
 
 
+def _fps_idx(npoint, pts):
+    return _memoized("fps", (pts,), int(npoint), lambda: tf_sampling.farthest_point_sample(npoint, pts.detach()))
+
+
 def sampling(npoint, pts, feature=None):
     """pts (B, N, D) -> sub_pts (B, npoint, D) [, sub_feature (B, npoint, C)] by farthest point sampling on pts
     (reference :33-49).  Differentiable w.r.t. pts / feature (tf.gather_nd semantics)."""
-    def run():
-        idx = tf_sampling.farthest_point_sample(npoint, pts.detach())
-        return idx, _ops.GatherRows.apply(pts, idx)
-    fps_idx, sub = _memoized("fps", (pts,), int(npoint), run)
+    fps_idx = _fps_idx(npoint, pts)
+    sub = _ops.GatherRows.apply(pts, fps_idx)
     if feature is None:
         return sub
     return sub, _ops.GatherRows.apply(feature, fps_idx)
 
 
-def _neighbor_idx(K, src_xyz, q_xyz, use_knn, radius):
+def _neighbor_idx(K, src_xyz, q_xyz, use_knn, radius, q_key=None):
+    """q_key: the tensor that identifies the query set for memoisation (the FPS index the queries were gathered with:
+    two gathers of the same rows are different tensor objects but the same queries)."""
     def run():
         if use_knn:
             return knn_query(K, src_xyz.detach(), q_xyz.detach())
         return tf_grouping.query_ball_point(radius, K, src_xyz.detach(), q_xyz.detach())[0]
-    return _memoized("nbr", (src_xyz, q_xyz), (int(K), bool(use_knn), radius), run)
+    return _memoized("nbr", (src_xyz, q_xyz if q_key is None else q_key), (int(K), bool(use_knn), radius), run)
 
 
 def grouping(feature, K, src_xyz, q_xyz, use_xyz=True, use_knn=True, radius=0.2):
@@ -200,10 +219,11 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
         batch_size, num_points, num_channel = feature.shape
         sampled = num_points != npoint
         if sampled:
-            new_xyz, new_feature = sampling(npoint, xyz, feature)        # FPS + row gathers
+            fps_idx = _fps_idx(npoint, xyz)                               # FPS + row gathers (sampling(), :33-49)
+            new_xyz, new_feature = _ops.GatherRows.apply(xyz, fps_idx), _ops.GatherRows.apply(feature, fps_idx)
         else:
-            new_xyz, new_feature = xyz, feature
-        idx = _neighbor_idx(nsample, xyz, new_xyz, use_knn, radius)       # (B, npoint, nsample) int32
+            fps_idx, new_xyz, new_feature = None, xyz, feature
+        idx = _neighbor_idx(nsample, xyz, new_xyz, use_knn, radius, q_key=fps_idx)   # (B, npoint, nsample) int32
         nl_channel = mlp[-1]
 
         if sampled:                                                        # Adaptive Sampling (reference :246-247)

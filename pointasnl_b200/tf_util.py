@@ -34,8 +34,11 @@ class VariableStore(torch.nn.Module):
     """TF1-style variable store: ``get_variable`` creates a Parameter (or buffer) under the current scope path on
     first use and returns the existing one afterwards."""
 
-    def __init__(self, device="cuda", seed=0):
+    def __init__(self, device="cuda", seed=0, init_fn=None):
+        """init_fn(full_name, shape, leaf_name) -> array-like or None: overrides the initialisers (used to load
+        name-seeded golden values or an imported checkpoint at creation time)."""
         super().__init__()
+        self.init_fn = init_fn
         self.device = torch.device(device)
         self._scope = []
         self._gen = torch.Generator(device="cpu")
@@ -68,7 +71,12 @@ class VariableStore(torch.nn.Module):
             if tuple(v.shape) != tuple(shape):
                 raise ValueError(f"variable {full} exists with shape {tuple(v.shape)}, requested {tuple(shape)}")
             return v
-        value = init(tuple(shape), self._gen).to(self.device)
+        value = None
+        if self.init_fn is not None:
+            value = self.init_fn(full, tuple(shape), name)
+        if value is None:
+            value = init(tuple(shape), self._gen)
+        value = torch.as_tensor(value).to(torch.float32).reshape(tuple(shape)).to(self.device)
         if trainable:
             self.register_parameter(key, torch.nn.Parameter(value))
         else:

@@ -1,0 +1,225 @@
+"""The CUDA path against vectors produced by the REFERENCE'S OWN PYTHON (tests/golden/tf_graph_*.npz: the reference's
+utils/pointasnl_util.py, utils/pointnet_util.py, utils/tf_util.py and both model files executed unmodified on the
+stand-in tensorflow module tests/golden/tf_shim.py, fp64; generator tests/golden/make_golden_tf.py).  No restatement
+sits between the product and the reference here: same inputs, same name-seeded variables (oracle/golden_init.py),
+outputs / loss / the gradient digest of every variable compared.
+
+Bars (fp32 device arithmetic vs an fp64 reference run): layer outputs within 5e-4 of the largest output value, model
+logits within 2e-3, losses 1e-4 relative, gradient digests within 2 % of the gradient's norm (the same bars as
+tests/test_gpu_model.py, whose header explains where they come from); discrete decisions are bit-exact by
+construction of the inputs (fp32 coordinates).
+"""
+import contextlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.golden_init import digest, golden_init, probe_weights
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def dev(a, cuda, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    return t.requires_grad_(True) if grad else t
+
+
+def new_store(cuda):
+    from pointasnl_b200 import tf_util
+    return tf_util.VariableStore(cuda, seed=0, init_fn=lambda full, shape, leaf: golden_init(full, shape, leaf))
+
+
+@contextlib.contextmanager
+def no_dropout():
+    from pointasnl_b200 import tf_util
+    orig = tf_util.dropout
+    tf_util.dropout = lambda inputs, is_training, scope, keep_prob=0.5, noise_shape=None: inputs
+    try:
+        yield
+    finally:
+        tf_util.dropout = orig
+
+
+def probe(x, name):
+    return (x * torch.from_numpy(probe_weights(name, x.shape)).to(x)).sum()
+
+
+def close(got, want, bar, what):
+    got = got.detach().double().cpu().numpy()
+    want = np.asarray(want, dtype=np.float64)
+    err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+    print(f"   {what}: max error {err:.2e} of the largest value (bar {bar:g})")
+    assert err <= bar, f"{what}: {err:.3e} > {bar:g}"
+
+
+def check_grads(gold, prefix, named, tol=2e-2):
+    """named: name -> tensor whose .grad was just populated.  Every digest in the golden file must be matched."""
+    want_names = {k[len(prefix) + 5:] for k in gold.files if k.startswith(prefix + "grad/")}
+    assert want_names == set(named), sorted(want_names ^ set(named))
+    scale = max(float(gold[prefix + "grad/" + n][1]) for n in named)
+    worst = (0.0, None)
+    for n, t in named.items():
+        want = gold[prefix + "grad/" + n]
+        g = np.zeros(tuple(t.shape)) if t.grad is None else t.grad.detach().double().cpu().numpy()
+        got = digest(n, g)
+        norm = float(want[1])
+        bar = tol * norm + 1e-5 * scale          # analytically-zero gradients: absolute floor, cf. test_gpu_model.py
+        errs = np.abs(got - want) / np.array([bar * np.sqrt(g.size), bar, 3 * bar])
+        if errs.max() > worst[0]:
+            worst = (float(errs.max()), n)
+    print(f"   gradients: worst digest error / bar = {worst[0]:.3f} ({worst[1]}) over {len(named)} tensors")
+    assert worst[0] < 1.0, worst
+
+
+def check_moving(gold, prefix, store, rtol=1e-4):
+    keys = [k for k in gold.files if k.startswith(prefix + "moving/")]
+    assert keys
+    v = store.variables()
+    for k in keys:
+        name = k[len(prefix) + 7:]
+        got = v[name].detach().double().cpu().numpy()
+        np.testing.assert_allclose(got, gold[k], rtol=rtol, atol=1e-6, err_msg=name)
+
+
+def named_with_inputs(store, **inputs):
+    d = {n: v for n, v in store.variables().items() if v.requires_grad}
+    d.update({"in/" + k: t for k, t in inputs.items()})
+    return d
+
+
+def test_adaptive_sampling_vs_reference_python(cuda):
+    from pointasnl_b200.pointasnl_util import AdaptiveSampling
+    g = load("tf_graph_adaptive_sampling.npz")
+    store = new_store(cuda)
+    xyz, feat = dev(g["group_xyz"], cuda, True), dev(g["group_feature"], cuda, True)
+    with store.as_default():
+        new_xyz, new_feature = AdaptiveSampling(xyz, feat, 6, True, 0.9, None, "as", True)
+    close(new_xyz, g["new_xyz"], 1e-4, "new_xyz")
+    close(new_feature, g["new_feature"], 1e-4, "new_feature")
+    (probe(new_xyz, "as/new_xyz") + probe(new_feature, "as/new_feature")).backward()
+    check_grads(g, "", named_with_inputs(store, group_xyz=xyz, group_feature=feat))
+    check_moving(g, "", store)
+
+
+def test_nonlocal_cell_vs_reference_python(cuda):
+    from pointasnl_b200.pointasnl_util import PointNonLocalCell
+    g = load("tf_graph_nonlocal.npz")
+    store = new_store(cuda)
+    f, p = dev(g["feature"], cuda, True), dev(g["new_point"], cuda, True)
+    with store.as_default():
+        out = PointNonLocalCell(f, p, [32, 48], True, 0.9, None, "nl", True)
+    close(out, g["out"], 5e-4, "out")
+    probe(out, "nl/out").backward()
+    check_grads(g, "", named_with_inputs(store, feature=f, new_point=p))
+    check_moving(g, "", store)
+
+
+@pytest.mark.parametrize("tag,npoint,nsample,mlp,as_nb,nl", [("as0", 40, 16, [16, 16, 32], 0, True),
+                                                              ("as6", 40, 16, [16, 16, 32], 6, True),
+                                                              ("self", 160, 16, [32, 32], 0, False)])
+def test_set_abstraction_vs_reference_python(cuda, tag, npoint, nsample, mlp, as_nb, nl):
+    from pointasnl_b200.pointasnl_util import PointASNLSetAbstraction
+    g = load("tf_graph_set_abstraction.npz")
+    store = new_store(cuda)
+    xyz, feat = dev(g["xyz"], cuda, True), dev(g["feature"], cuda, True)
+    with store.as_default():
+        new_xyz, new_point = PointASNLSetAbstraction(xyz, feat, npoint, nsample, mlp, True, 0.9, None, "layer1",
+                                                     as_neighbor=as_nb, NL=nl)
+    close(new_xyz, g[tag + "/new_xyz"], 1e-5, "new_xyz")
+    close(new_point, g[tag + "/new_point"], 5e-4, "new_point")
+    y = probe(new_point, tag + "/new_point")
+    if as_nb > 0:
+        y = y + probe(new_xyz, tag + "/new_xyz")
+    y.backward()
+    check_grads(g, tag + "/", named_with_inputs(store, xyz=xyz, feature=feat))
+    check_moving(g, tag + "/", store)
+
+
+def test_fp_module_vs_reference_python(cuda):
+    from pointasnl_b200.pointnet_util import pointnet_fp_module
+    g = load("tf_graph_fp_module.npz")
+    store = new_store(cuda)
+    p1, p2 = dev(g["points1"], cuda, True), dev(g["points2"], cuda, True)
+    with store.as_default():
+        out = pointnet_fp_module(dev(g["xyz1"], cuda), dev(g["xyz2"], cuda), p1, p2, [32, 24], True, 0.9, "fa", bn=True)
+    close(out, g["out"], 5e-4, "out")
+    probe(out, "fa/out").backward()
+    check_grads(g, "", named_with_inputs(store, points1=p1, points2=p2))
+
+
+def test_decoding_layer_vs_reference_python(cuda):
+    from pointasnl_b200.pointasnl_util import PointASNLDecodingLayer
+    g = load("tf_graph_decoding_layer.npz")
+    store = new_store(cuda)
+    p1, p2 = dev(g["points1"], cuda, True), dev(g["points2"], cuda, True)
+    with store.as_default():
+        out = PointASNLDecodingLayer(dev(g["xyz1"], cuda), dev(g["xyz2"], cuda), p1, p2, 8, [32, 24], True, 0.9, None,
+                                     "up", NL=False)
+    close(out, g["out"], 5e-4, "out")
+    probe(out, "up/out").backward()
+    check_grads(g, "", named_with_inputs(store, points1=p1, points2=p2))
+
+
+@pytest.mark.parametrize("tag", ["dense", "sparse"])
+def test_repulsion_loss_value_and_gradient_vs_reference_python(cuda, tag):
+    from pointasnl_b200.pointasnl_util import get_repulsion_loss
+    g = load("tf_graph_repulsion.npz")
+    pred = dev(g[tag + "/pred"], cuda, True)
+    loss = get_repulsion_loss(pred, nsample=20, radius=float(g[tag + "/radius"]))
+    loss.backward()
+    want = float(g[tag + "/loss"])
+    print(f"   loss {float(loss):.8f} vs {want:.8f}")
+    assert abs(float(loss) - want) <= 1e-5 * abs(want) + 1e-7
+    gw = g[tag + "/grad"]
+    err = np.abs(pred.grad.double().cpu().numpy() - gw).max() / np.abs(gw).max()
+    print(f"   grad max error {err:.2e} of the largest entry")
+    assert err <= 1e-4
+
+
+@pytest.mark.parametrize("tag,adaptive,uw", [("plain", False, 0.0), ("as", True, 0.0), ("as_uniform", True, 0.5)])
+def test_cls_model_vs_reference_python(cuda, tag, adaptive, uw):
+    """models/pointasnl_cls.py get_model + get_loss (BASELINE configs 2 and 3 at reduced size), --AS on and off, and
+    with the repulsion term switched on."""
+    from pointasnl_b200.callers import pointasnl_cls
+    g = load("tf_graph_cls.npz")
+    store = new_store(cuda)
+    with store.as_default(), no_dropout():
+        pred, end_points = pointasnl_cls.get_model(dev(g["point_cloud"], cuda), True, use_normal=True, bn_decay=0.9,
+                                                   adaptive_sample=adaptive)
+        loss = pointasnl_cls.get_loss(pred, dev(g["label"].astype(np.int64), cuda), end_points, uniform_weight=uw)
+    loss.backward()
+    close(end_points["l1_xyz"], g[tag + "/l1_xyz"], 1e-5, "l1_xyz")
+    close(pred, g[tag + "/pred"], 2e-3, "logits")
+    want = float(g[tag + "/loss"])
+    assert abs(float(loss) - want) <= 1e-4 * abs(want), (float(loss), want)
+    check_grads(g, tag + "/", {n: v for n, v in store.variables().items() if v.requires_grad})
+    if tag == "plain":
+        check_moving(g, tag + "/", store)
+
+
+@pytest.mark.parametrize("tag,fc,ncls,radius", [("scannet", 3, 21, 0.07), ("kitti", 1, 20, 0.2)])
+def test_seg_res_model_vs_reference_python(cuda, tag, fc, ncls, radius):
+    """models/pointasnl_sem_seg_res.py get_model + get_loss end to end (encoder, decoder, loss incl. the repulsion term
+    and the reference's double-counted classification loss), feature_channel = 3 (ScanNet rgb) and 1 (KITTI remission):
+    logits of the whole cloud and the gradient of EVERY variable, decoder included."""
+    from pointasnl_b200.callers import pointasnl_sem_seg_res as seg
+    g = load("tf_graph_seg.npz")
+    store = new_store(cuda)
+    with store.as_default(), no_dropout():
+        pred, end_points = seg.get_model(dev(g[tag + "/points"], cuda), True, ncls, bn_decay=0.9, feature_channel=fc)
+        loss = seg.get_loss(pred, dev(g[tag + "/label"].astype(np.int64), cuda), end_points,
+                            dev(g[tag + "/smpw"], cuda), radius=radius)
+    loss.backward()
+    close(end_points["l1_xyz"], g[tag + "/l1_xyz"], 1e-4, "l1_xyz")
+    close(pred[:, ::16], g[tag + "/pred_strided"], 3e-3, "logits (every 16th point)")
+    want = float(g[tag + "/loss"])
+    print(f"   loss {float(loss):.6f} vs {want:.6f}")
+    assert abs(float(loss) - want) <= 2e-4 * abs(want), (float(loss), want)
+    check_grads(g, tag + "/", {n: v for n, v in store.variables().items() if v.requires_grad})

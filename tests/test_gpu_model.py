@@ -88,7 +88,7 @@ def test_sa_layer_with_adaptive_sampling_matches_oracle(cuda):
     check_param_grads(grads, og)
 
 
-@pytest.mark.parametrize("adaptive_sample", [False])
+@pytest.mark.parametrize("adaptive_sample", [False, True])
 def test_cls_model_forward_backward_matches_oracle(cuda, adaptive_sample):
     """BASELINE config 2 at reduced batch: pointasnl_cls fwd + loss + bwd on (8, 1024, 6)."""
     from pointasnl_b200 import tf_util
