@@ -35,7 +35,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cls", choices=["cls", "seg"])
+    ap.add_argument("--workload", default="cls", choices=["cls", "seg", "kitti"],
+                    help="cls = configs[1] (configs[2] with --AS); seg = configs[3] (ScanNet grid shape, B=4 N=10240, rgb); "
+                         "kitti = configs[4] (SemanticKITTI grid shape, B=2 N=65536, remission)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch clouds PER GPU; strong: --batch clouds in total, sharded over the ranks "
+                         "(per-replica batch-norm statistics: not the single-GPU model at the same global batch)")
     ap.add_argument("--AS", action="store_true", help="adaptive sampling on (BASELINE configs[2])")
     ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default 32 cls / 4 seg)")
     ap.add_argument("--points", type=int, default=None)
@@ -59,8 +64,19 @@ def make_batch(workload, batch, points, seed):
     if workload == "cls":
         pc, labels = synth.modelnet_batch(batch, points, seed)
         return pc, labels, None
+    if workload == "kitti":
+        pts, labels = synth.kitti_batch(batch, points, seed)
+        return pts, labels, np.random.default_rng(seed).uniform(1.0, 4.9, labels.shape).astype(np.float32)
     pts, labels, smpw = synth.scannet_batch(batch, points, seed)
     return pts, labels, smpw
+
+
+# model / data configuration of each workload: TrainStep kwargs, default batch per GPU, default points
+WORKLOADS = {
+    "cls": dict(model="cls", batch=32, points=1024, kw={}),
+    "seg": dict(model="seg", batch=4, points=10240, kw=dict(num_class=21, feature_channel=3, radius=0.07)),
+    "kitti": dict(model="seg", batch=2, points=65536, kw=dict(num_class=20, feature_channel=1, radius=0.2)),
+}
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
@@ -246,7 +262,7 @@ def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0):
     Returns (clouds_per_s, ms_per_step, threads_used, kind, sample description)."""
     from oracle import cref, model_ref, refnative
     cores = os.cpu_count() or 1
-    sample_batch = min(batch, 8 if args.workload == "cls" else 1)
+    sample_batch = min(batch, 8 if args.workload == "cls" else (2 if args.workload == "seg" else 1))
     pc, labels, smpw = make_batch(args.workload, sample_batch, points, 1)
     x = torch.from_numpy(pc)
     y = torch.from_numpy(labels)
@@ -255,7 +271,9 @@ def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0):
     def fwd():
         if args.workload == "cls":
             return model_ref.cls_forward(r, x, y, use_normal=True, adaptive_sample=args.AS)[1]
-        return model_ref.seg_forward(r, x, 21, y, torch.from_numpy(smpw), feature_channel=3)[1]
+        kw = WORKLOADS[args.workload]["kw"]
+        return model_ref.seg_forward(r, x, kw["num_class"], y, torch.from_numpy(smpw),
+                                     feature_channel=kw["feature_channel"], radius=kw["radius"])[1]
 
     torch.set_num_threads(min(cores, 16))
     with torch.no_grad():
@@ -309,13 +327,25 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    batch = args.batch or (32 if args.workload == "cls" else 4)
-    points = args.points or (1024 if args.workload == "cls" else 10240)
-    workload_name = ("pointasnl_cls" + ("+AS" if args.AS else "") if args.workload == "cls" else "pointasnl_sem_seg_res") \
-        + f" B={batch} N={points} per GPU, synthetic"
-    metric = METRIC if args.workload == "cls" else f"point-clouds/sec fwd+bwd pointasnl_sem_seg_res B={batch} N={points}"
+    wl = WORKLOADS[args.workload]
+    batch = args.batch or wl["batch"]
+    points = args.points or wl["points"]
+    global_batch = batch * world
+    if args.scaling == "strong":          # --batch clouds in total; rank r takes dp.shard_range(batch, r, world)
+        from pointasnl_b200 import dp as _dp
+        global_batch = batch
+        lo, hi = _dp.shard_range(global_batch, rank, world)
+        batch = hi - lo
+        if batch < 2:
+            raise SystemExit(f"strong scaling: rank {rank} would get {batch} cloud(s); batch norm needs >= 2 per replica")
+    model_name = {"cls": "pointasnl_cls" + ("+AS" if args.AS else ""), "seg": "pointasnl_sem_seg_res (ScanNet grid, rgb)",
+                  "kitti": "pointasnl_sem_seg_res (SemanticKITTI grid, remission)"}[args.workload]
+    workload_name = model_name + (f" B={batch} N={points} per GPU" if args.scaling == "weak" else
+                                  f" global B={global_batch} N={points} sharded over {world} GPU(s)") + ", synthetic"
+    metric = METRIC if args.workload == "cls" else f"point-clouds/sec fwd+bwd pointasnl_sem_seg_res B={wl['batch']} N={points}"
     config = {"workload": workload_name, "step": "forward + loss + backward + grad all-reduce + Adam",
-              "parallelism": f"dp{world}", "global_batch": batch * world}
+              "parallelism": f"dp{world}", "global_batch": global_batch,
+              "batch_norm": "per-replica statistics" if world > 1 else "single replica"}
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -326,7 +356,7 @@ def main():
         warm = 0
         val, ms, cores, kind, sample = run_cpu_reference(args, batch, points, steps, warm)
         line = {"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -348,7 +378,7 @@ def main():
     h_pc = torch.from_numpy(pc).pin_memory()
     h_lab = torch.from_numpy(labels).pin_memory()
     h_w = torch.from_numpy(smpw).pin_memory() if smpw is not None else None
-    ts = TrainStep(args.workload, batch, points, dev, adaptive_sample=args.AS, use_graph=not args.no_graph, seed=0)
+    ts = TrainStep(wl["model"], batch, points, dev, adaptive_sample=args.AS, use_graph=not args.no_graph, seed=0, **wl["kw"])
     ts.set_inputs(h_pc, h_lab, h_w)
     torch.cuda.synchronize()
     if not args.no_graph:
@@ -384,7 +414,7 @@ def main():
         barrier()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = dp.max_over_ranks(sum(step_ms), dev)
-    value = batch * world * args.steps / (total_ms * 1e-3)
+    value = global_batch * args.steps / (total_ms * 1e-3)
 
     # ---- timed region 2: end to end from pinned host memory, loss read back every step
     e2e_t = []
@@ -399,7 +429,7 @@ def main():
     barrier()
     assert np.isfinite(loss_host)
     e2e_total = dp.max_over_ranks(sum(e2e_t), dev)
-    e2e_value = batch * world * args.steps / e2e_total
+    e2e_value = global_batch * args.steps / e2e_total
     h2d = h_pc.numel() * 4 + h_lab.numel() * 8 + (h_w.numel() * 4 if h_w is not None else 0)
 
     if rank != 0:
@@ -412,7 +442,7 @@ def main():
     prof_steps = min(args.steps, 5)
     ts_prof = ts if args.no_graph else None
     if ts_prof is None:
-        ts_prof = TrainStep(args.workload, batch, points, dev, adaptive_sample=args.AS, use_graph=False, seed=0)
+        ts_prof = TrainStep(wl["model"], batch, points, dev, adaptive_sample=args.AS, use_graph=False, seed=0, **wl["kw"])
         ts_prof.bucket.all_reduce_mean = lambda *a, **k: None   # rank-0 only pass: no collective
         ts_prof.set_inputs(h_pc, h_lab, h_w)
         for _ in range(2):
@@ -464,7 +494,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {**config, "l2": "flushed (256 MiB memset) before every timed step, outside the event pair",
                        "launch": "eager" if args.no_graph else "CUDA graphs (fwd+bwd, Adam) around one NCCL all-reduce"},

@@ -169,12 +169,14 @@ int pasnl_nl_core_bwd(int b, int s, int n, int d, const float *q, const float *k
  * The conv bias cancels inside batch norm, so it is NOT added to y: `bias` (c) or NULL is only used to keep
  * moving_mean equal to what TF would store (mean(y) + bias).  act: 0 none, 1 relu, 2 leaky_relu(0.2).
  * Outputs: out (rows, c); mean (c) = mean(y); var (c) = biased variance (both kept for the backward);
- * running_mean / running_var (c) or NULL are updated in place: r = decay*r + (1-decay)*batch.
+ * running_mean / running_var (c) or NULL are updated in place: r = decay*r + (1-decay)*batch; with
+ * unbiased_moving_var != 0 the moving variance is fed var * rows/(rows-1) (TF's fused batch-norm kernel, which
+ * tf.contrib.layers.batch_norm takes for rank-2 / rank-4 inputs: fully_connected and conv2d), else the biased one (conv1d).
  * workspace: pasnl_bn_workspace_bytes(c) bytes. */
 size_t pasnl_bn_workspace_bytes(int c);
 int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *gamma, const float *beta, float eps, int act,
                      float *out, float *mean, float *var, const float *bias, float *running_mean, float *running_var,
-                     float decay, int stats_ready, void *workspace, void *stream);
+                     float decay, int unbiased_moving_var, int stats_ready, void *workspace, void *stream);
 /* stats_ready != 0: `workspace` already holds the per-channel sum (c doubles) and sum of squares (c doubles) of y,
  * accumulated by pasnl_gemm_rows_tf32x3's epilogue (col_stats): the statistics pass over y is skipped. */
 /* Backward of the above: dout (rows, c) -> dy (rows, c) (the gradient w.r.t. the GEMM output), dgamma (c), dbeta (c). */
@@ -193,6 +195,18 @@ int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, co
 /* col_stats: NULL, or 2*n doubles (zeroed by the caller) into which the epilogue adds the per-column sum and sum of
  * squares of C -- the batch-norm statistics, obtained without another pass over C. */
 
+/* The same product for the tall layers whose weights fit ONE TMEM-resident tile (k <= 128, n <= 128, rows >= 2*128*SMs,
+ * A 16-byte aligned with lda % 4 == 0): activations streamed by TMA tensor copies, W^T stationary in TMEM, C^T
+ * accumulated so that column statistics are thread-local (csrc/gemm_ws.cu).  pasnl_gemm_rows_tf32x3 routes eligible
+ * problems here by itself; the direct entry point additionally takes W in its stored [k][n] layout (w_kn != 0: no
+ * transpose pass) and an optional prologue f(a) = act(a * pro_scale[col] + pro_shift[col]) on the A operand
+ * (pro_act 0 none / 1 relu / 2 leaky_relu(0.2)): the batch-norm normalise + activation of the producing layer, applied
+ * on the way into the tensor core instead of in a pass of its own (utils/tf_util.py:170-185). */
+int pasnl_gemm_rows_ws_eligible(long rows, int k, int n, const void *A, long lda);
+int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long lda, const float *W, long ldw, int w_kn, float *C,
+                       long ldc, double *col_stats, const float *pro_scale, const float *pro_shift, int pro_act,
+                       void *stream);
+
 /* Weight gradient of the same layers (replaces the tf.matmul / conv2d filter gradients TF autodiff emits):
  *     dW[m, n] = sum_r X[r, m] * Y[r, n] ,   X (rows, m), Y (rows, n), dW (m, n) row-major, ldw == n.
  * X = layer input, Y = gradient w.r.t. the GEMM output.  tcgen05, 3xTF32, operands transposed on the way into shared memory,
@@ -200,6 +214,48 @@ int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, co
  * here unless dw_zeroed != 0 (the caller passes memory that is already all-zero, e.g. a slice of a per-step arena). */
 int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
                             long ldw, int dw_zeroed, void *stream);
+
+/* ---------------------------------------------------------------- launch-bound glue of a training step (csrc/small_ops.cu)
+ * The callers' classifier head, residual adds, channel concats, dropout, losses and optimizer as library kernels, so
+ * that a step contains no cuBLAS / ATen kernel.  Reference: utils/tf_util.py:318-355,590-615;
+ * utils/pointasnl_util.py:283-285; utils/pointnet_util.py:218; models/pointasnl_cls.py:55-70;
+ * models/pointasnl_sem_seg_res.py:72-88; train.py:150-155 (tf.train.AdamOptimizer). */
+
+/* out (rows <= 64, nj) += in (rows, ni) . M, with M(i, j) = W[i*ldw + j] (w_transposed == 0: y = x.W, W stored [k][n]) or
+ * W[j*ldw + i] (w_transposed != 0: dx = dy.W^T with the same stored W).  `out` must be zero-initialised by the caller
+ * (the split contraction is reduced with atomics). */
+int pasnl_gemm_skinny(int rows, int ni, int nj, const float *in, long ldin, const float *W, long ldw, int w_transposed,
+                      float *out, long ldout, void *stream);
+/* dW (ni, nj) = x (rows <= 64, ni)^T . dy (rows, nj): every element written. */
+int pasnl_wgrad_skinny(int rows, int ni, int nj, const float *x, long ldx, const float *dy, long ldy, float *dW, long ldw,
+                       void *stream);
+/* out = a + b (+ c when c != NULL), n elements (tf.add chains of the layer functions). */
+int pasnl_add_n(long n, const float *a, const float *b, const float *c, float *out, void *stream);
+/* out (rows, ca+cb) = [a | b] along the channel axis (tf.concat(axis=-1)); split = its gradient (ga / gb may be NULL). */
+int pasnl_concat_cols(long rows, int ca, int cb, const float *a, long lda, const float *b, long ldb, float *out,
+                      void *stream);
+int pasnl_split_cols(long rows, int ca, int cb, const float *g, float *ga, float *gb, void *stream);
+/* tf.nn.dropout: out = x / keep_prob where u(seed, *step, index) < keep_prob, else 0.  The mask is a pure function of
+ * (seed, *step, index): call again with the incoming gradient as x for the backward pass.  step (device, may be NULL)
+ * is the optimizer's step counter, so that replays of a captured graph draw fresh masks. */
+int pasnl_dropout(long n, const float *x, float keep_prob, unsigned long long seed, const long *step, float *out,
+                  void *stream);
+/* Sparse soft-max cross entropy, value and gradient.  weights == NULL: loss = out_scale * mean_r ce_r (tf.reduce_mean of
+ * sparse_softmax_cross_entropy_with_logits); else loss = out_scale * sum_r w_r ce_r / max(#{w_r != 0}, 1)
+ * (tf.losses.sparse_softmax_cross_entropy, SUM_BY_NONZERO_WEIGHTS).  labels are int64.  fwd writes lse (rows) and the
+ * workspace the backward reads; bwd: dlogits = *grad_loss * d loss / d logits. */
+size_t pasnl_softmax_ce_workspace_bytes(void);
+int pasnl_softmax_ce_fwd(long rows, int c, const float *logits, const long *labels, const float *weights, float out_scale,
+                         float *lse, void *workspace, float *loss, void *stream);
+int pasnl_softmax_ce_bwd(long rows, int c, const float *logits, const long *labels, const float *weights, float out_scale,
+                         const float *lse, const void *workspace, const float *grad_loss, float *dlogits, void *stream);
+/* One Adam step (TF formulation) over a flat parameter buffer with the L2 regulariser folded in: for elements with
+ * l2_mask != 0 the gradient gets + l2_coeff * p and *reg_loss (double, may be NULL) += l2_coeff * p^2 / 2 (pre-update
+ * values).  g is multiplied by grad_scale first (1/world after a summed all-reduce).  *step (device int64) is the number
+ * of steps taken so far; it is incremented on the stream after the update. */
+int pasnl_adam_l2(long n, float *p, const float *g, float *m, float *v, const unsigned char *l2_mask, float l2_coeff,
+                  float grad_scale, float lr, float beta1, float beta2, float eps, long *step, double *reg_loss,
+                  void *stream);
 
 #ifdef __cplusplus
 }

@@ -45,9 +45,21 @@ SIGNATURES = {
     "pasnl_nl_core_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pasnl_nl_core_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P]),
     "pasnl_gemm_rows_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),
+    "pasnl_gemm_rows_ws_eligible": (c_int, [c_long, c_int, c_int, P, c_long]),
+    "pasnl_gemm_rows_ws": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, c_int, P, c_long, P, P, P, c_int, P]),
     "pasnl_gemm_wgrad_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, c_int, P]),
+    "pasnl_gemm_skinny": (c_int, [c_int, c_int, c_int, P, c_long, P, c_long, c_int, P, c_long, P]),
+    "pasnl_wgrad_skinny": (c_int, [c_int, c_int, c_int, P, c_long, P, c_long, P, c_long, P]),
+    "pasnl_add_n": (c_int, [c_long, P, P, P, P, P]),
+    "pasnl_concat_cols": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, P]),
+    "pasnl_split_cols": (c_int, [c_long, c_int, c_int, P, P, P, P]),
+    "pasnl_dropout": (c_int, [c_long, P, c_float, ctypes.c_ulonglong, P, P, P]),
+    "pasnl_softmax_ce_workspace_bytes": (c_size_t, []),
+    "pasnl_softmax_ce_fwd": (c_int, [c_long, c_int, P, P, P, c_float, P, P, P, P]),
+    "pasnl_softmax_ce_bwd": (c_int, [c_long, c_int, P, P, P, c_float, P, P, P, P, P]),
+    "pasnl_adam_l2": (c_int, [c_long, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P]),
     "pasnl_bn_workspace_bytes": (c_size_t, [c_int]),
-    "pasnl_bn_act_fwd": (c_int, [c_long, c_int, P, P, P, c_float, c_int, P, P, P, P, P, P, c_float, c_int, P, P]),
+    "pasnl_bn_act_fwd": (c_int, [c_long, c_int, P, P, P, c_float, c_int, P, P, P, P, P, P, c_float, c_int, c_int, P, P]),
     "pasnl_bn_act_bwd": (c_int, [c_long, c_int, P, P, P, P, P, P, c_float, c_int, P, P, P, c_int, P, P]),
 }
 
@@ -68,7 +80,8 @@ profiler = None    # optional object with before(name, args) / after(name, args)
 KERNELS_PER_CALL = {
     "pasnl_gather_point_grad": 2, "pasnl_gather_rows_grad": 2, "pasnl_group_point_grad": 2,
     "pasnl_three_interpolate_grad": 2, "pasnl_group_concat_grad": 4, "pasnl_nl_core_bwd": 3,
-    "pasnl_bn_act_fwd": 3, "pasnl_bn_act_bwd": 3, "pasnl_gemm_wgrad_tf32x3": 2,
+    "pasnl_bn_act_fwd": 3, "pasnl_bn_act_bwd": 3, "pasnl_gemm_wgrad_tf32x3": 2, "pasnl_softmax_ce_fwd": 2,
+    "pasnl_adam_l2": 2,
 }
 
 

@@ -577,7 +577,7 @@ class DenseBNAct(torch.autograd.Function):
     not added and its gradient is exactly zero."""
 
     @staticmethod
-    def forward(ctx, x, w2d, bias, gamma, beta, running_mean, running_var, decay, eps, act):
+    def forward(ctx, x, w2d, bias, gamma, beta, running_mean, running_var, decay, eps, act, unbiased_moving_var=True):
         cin, cout = w2d.shape
         x2 = x.reshape(-1, cin)
         if not x2.is_contiguous():
@@ -591,7 +591,7 @@ class DenseBNAct(torch.autograd.Function):
         var = torch.empty_like(mean)
         _call("pasnl_bn_act_fwd", rows, cout, _ptr(y), _ptr(gamma), _ptr(beta), float(eps), int(act), _ptr(out),
               _ptr(mean), _ptr(var), _ptr(bias), _ptr(running_mean), _ptr(running_var), float(decay),
-              1 if stats_ready else 0, _ptr(ws), _stream())
+              1 if unbiased_moving_var else 0, 1 if stats_ready else 0, _ptr(ws), _stream())
         if stats_ready or _bn_single_launch(rows, cout):
             _lib.launch_count -= 2      # no memset / statistics nodes (fused in the GEMM, or one cooperative launch)
         ctx.save_for_backward(x2, w2d, y, gamma, beta, mean, var)
@@ -622,4 +622,4 @@ class DenseBNAct(torch.autograd.Function):
         dx = gemm_rows(dy, w2d).reshape(xshape) if ctx.needs_input_grad[0] else None   # dy.W^T: Bt = W as stored
         dw = gemm_wgrad(x2, dy) if ctx.needs_input_grad[1] else None
         dbias = _zeros(gamma.shape, torch.float32, gamma.device)[0] if ctx.needs_input_grad[2] else None
-        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None

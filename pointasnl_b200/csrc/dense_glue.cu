@@ -126,7 +126,7 @@ template <int VEC>
 __device__ __forceinline__ void bn_apply_body(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                 const double *__restrict__ ws, int shifted, float *__restrict__ mean,
                                 float *__restrict__ var, const float *__restrict__ bias, float *__restrict__ running_mean,
-                                float *__restrict__ running_var, float decay, const float *__restrict__ gamma,
+                                float *__restrict__ running_var, float decay, float vcorr, const float *__restrict__ gamma,
                                 const float *__restrict__ beta, float eps, int act, float *__restrict__ out) {
     const int t = threadIdx.x, cv = t % cvec, ry = t / cvec;
     const int col = cv * VEC;
@@ -145,9 +145,11 @@ __device__ __forceinline__ void bn_apply_body(long rows, int c, int cvec, int rp
         if (blockIdx.x == 0 && ry == 0) {
             mean[ch] = mu[v];
             var[ch] = vf;
-            // moving averages as tf.contrib.layers.batch_norm keeps them (assign_moving_average, biased batch variance)
+            // moving averages as tf.contrib.layers.batch_norm keeps them (assign_moving_average).  vcorr = rows/(rows-1)
+            // when the TF layer takes the fused kernel (rank-2 / rank-4 inputs: the moving variance is fed the
+            // Bessel-corrected batch variance), 1 for the rank-3 conv1d layers (biased variance)
             if (running_mean) running_mean[ch] = decay * running_mean[ch] + (1.f - decay) * (mu[v] + (bias ? bias[ch] : 0.f));
-            if (running_var) running_var[ch] = decay * running_var[ch] + (1.f - decay) * vf;
+            if (running_var) running_var[ch] = decay * running_var[ch] + (1.f - decay) * vf * vcorr;
         }
     }
     const long chunk = (rows + gridDim.x - 1) / gridDim.x;
@@ -332,9 +334,9 @@ template <int VEC>
 __global__ void bn_apply_kernel(long rows, int c, int cvec, int rpb, const float *__restrict__ y,
                                 const double *__restrict__ ws, int shifted, float *__restrict__ mean,
                                 float *__restrict__ var, const float *__restrict__ bias, float *__restrict__ running_mean,
-                                float *__restrict__ running_var, float decay, const float *__restrict__ gamma,
+                                float *__restrict__ running_var, float decay, float vcorr, const float *__restrict__ gamma,
                                 const float *__restrict__ beta, float eps, int act, float *__restrict__ out) {
-    bn_apply_body<VEC>(rows, c, cvec, rpb, y, ws, shifted, mean, var, bias, running_mean, running_var, decay, gamma, beta,
+    bn_apply_body<VEC>(rows, c, cvec, rpb, y, ws, shifted, mean, var, bias, running_mean, running_var, decay, vcorr, gamma, beta,
                        eps, act, out);
 }
 template <int VEC>
@@ -361,14 +363,14 @@ template <int VEC>
 __global__ void __launch_bounds__(kMaxThreads) bn_fwd_coop_kernel(
     long rows, int c, int cvec, int rpb, const float *__restrict__ y, double *ws, float *__restrict__ mean,
     float *__restrict__ var, const float *__restrict__ bias, float *__restrict__ running_mean,
-    float *__restrict__ running_var, float decay, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+    float *__restrict__ running_var, float decay, float vcorr, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
     int act, float *__restrict__ out) {
     cg::grid_group grid = cg::this_grid();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * c; i += gridDim.x * blockDim.x) ws[i] = 0.0;
     grid.sync();
     bn_stats_body<VEC>(rows, c, cvec, rpb, y, ws);
     grid.sync();
-    bn_apply_body<VEC>(rows, c, cvec, rpb, y, ws, 1, mean, var, bias, running_mean, running_var, decay, gamma, beta, eps,
+    bn_apply_body<VEC>(rows, c, cvec, rpb, y, ws, 1, mean, var, bias, running_mean, running_var, decay, vcorr, gamma, beta, eps,
                        act, out);
 }
 template <int VEC>
@@ -431,7 +433,9 @@ extern "C" size_t pasnl_bn_workspace_bytes(int c) { return c > 0 ? sizeof(double
 
 extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *gamma, const float *beta, float eps,
                                 int act, float *out, float *mean, float *var, const float *bias, float *running_mean,
-                                float *running_var, float decay, int stats_ready, void *workspace, void *stream) {
+                                float *running_var, float decay, int unbiased_moving_var, int stats_ready,
+                                void *workspace, void *stream) {
+    const float vcorr = (unbiased_moving_var && rows > 1) ? (float)((double)rows / (double)(rows - 1)) : 1.f;
     PASNL_CHECK_ARG(rows >= 1 && c >= 1 && act >= 0 && act <= 2 && c <= 4096);
     PASNL_CHECK_ARG(y && gamma && beta && out && mean && var && workspace);
     cudaStream_t st = (cudaStream_t)stream;
@@ -443,9 +447,9 @@ extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *g
         // small layer, statistics not provided: clear + statistics + normalise/activate in one cooperative launch
         long rows_ = rows;
         int c_ = c, cvec_ = s.cvec, rpb_ = s.rpb, act_ = act;
-        float eps_ = eps, decay_ = decay;
+        float eps_ = eps, decay_ = decay, vcorr_ = vcorr;
         void *args[] = {&rows_, &c_, &cvec_, &rpb_, (void *)&y, &ws, &mean, &var, (void *)&bias, &running_mean,
-                        &running_var, &decay_, (void *)&gamma, (void *)&beta, &eps_, &act_, &out};
+                        &running_var, &decay_, &vcorr_, (void *)&gamma, (void *)&beta, &eps_, &act_, &out};
         const void *fn = s.vec == 4 ? (const void *)bn_fwd_coop_kernel<4> : (const void *)bn_fwd_coop_kernel<1>;
         cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(coop_grid(rows, s.rpb)), dim3(s.threads), args, smem, st);
         if (ce != cudaSuccess) return (int)ce;
@@ -460,11 +464,11 @@ extern "C" int pasnl_bn_act_fwd(long rows, int c, const float *y, const float *g
     if (s.vec == 4) {
         if (!stats_ready) bn_stats_kernel<4><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
         bn_apply_kernel<4><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, ws, stats_ready ? 0 : 1, mean, var, bias,
-                                                     running_mean, running_var, decay, gamma, beta, eps, act, out);
+                                                     running_mean, running_var, decay, vcorr, gamma, beta, eps, act, out);
     } else {
         if (!stats_ready) bn_stats_kernel<1><<<rg, s.threads, smem, st>>>(rows, c, s.cvec, s.rpb, y, ws);
         bn_apply_kernel<1><<<ag, s.threads, 0, st>>>(rows, c, s.cvec, s.rpb, y, ws, stats_ready ? 0 : 1, mean, var, bias,
-                                                     running_mean, running_var, decay, gamma, beta, eps, act, out);
+                                                     running_mean, running_var, decay, vcorr, gamma, beta, eps, act, out);
     }
     return pasnl_launch_status();
 }

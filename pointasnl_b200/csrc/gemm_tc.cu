@@ -1344,6 +1344,9 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
     if (rows == 0) return PASNL_OK;
     PASNL_CHECK_ARG(A && Bt && C && rows / 128 < 2147483647L && n <= 256 * 65535);
     cudaStream_t st = (cudaStream_t)stream;
+    // tall layers whose weights fit one TMEM-resident tile: TMA-fed, weights-stationary kernel (gemm_ws.cu)
+    if (pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda))
+        return pasnl_gemm_rows_ws(rows, k, n, A, lda, Bt, ldb, 0, C, ldc, col_stats, nullptr, nullptr, 0, stream);
     // many row tiles per SM and small weights: persistent kernel with the weights resident in shared memory
     // (one launch covers up to 160 output columns, so the 134-wide grouped-feature layers stay single-pass)
     const int kpad = (k + gtc::kKC - 1) / gtc::kKC * gtc::kKC;

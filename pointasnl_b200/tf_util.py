@@ -5,17 +5,17 @@ graph ops that create variables by *scope name* (tf.variable_scope / tf.get_vari
 ``pointasnl_util.PointASNLSetAbstraction(xyz, feature, ..., scope, ...)`` and friends drop-in at the signature
 level, this module reproduces exactly that: a ``VariableStore`` (an nn.Module) in which variables are created on
 first use under the same nested scope names TF would give them (``layer1/layer1/conv_kv/weights`` ...), and reused
-afterwards (AUTO_REUSE).  Dense math itself is plain PyTorch (cuBLAS): it is NOT part of the hot path this repo
-re-implements -- only the call semantics matter: bias -> batch norm -> activation order
+afterwards (AUTO_REUSE).  Call semantics follow the reference: bias -> batch norm -> activation order
 (reference tf_util.py:170-185), NHWC layout, xavier init, BN eps 1e-3 with biased batch variance (:512-531).
 
-On CUDA tensors in training mode the sequence matmul -> bias -> batch norm -> activation runs as two cuBLAS GEMMs
-around the fused pasnl epilogue kernels (csrc/dense_glue.cu, `_ops.DenseBNAct`): two passes over the activation
-forward and two backward instead of ~8 / ~9.  The op-by-op path below remains for CPU tensors (unit tests of this
-mirror) and inference mode, and is checked against the fused path on the GPU (tests/test_gpu_glue.py).
+On CUDA tensors in training mode the sequence matmul -> bias -> batch norm -> activation runs on the library's
+tcgen05 3xTF32 GEMMs (csrc/gemm_tc.cu) and fused batch-norm kernels (csrc/dense_glue.cu) through `_ops.DenseBNAct`
+(SURVEY.md 8f rank 2).  The op-by-op PyTorch path below remains for CPU tensors (unit tests of this mirror) and
+inference mode, and is checked against the fused path on the GPU (tests/test_gpu_glue.py).
 
-Documented deviations: on the op-by-op path moving_variance is updated with torch's unbiased batch variance (TF's
-non-fused contrib batch_norm, and the fused path here, use the biased one); inference-mode statistics only.
+Moving averages follow tf.contrib.layers.batch_norm(updates_collections=None): moving = decay*moving +
+(1-decay)*batch, with the Bessel-corrected batch variance for conv2d / fully_connected (TF's fused kernel) and the
+biased one for conv1d (rank-3 inputs); pinned by tests/golden/tf_graph_*.npz (`moving/...` entries).
 """
 import contextlib
 import math
@@ -205,7 +205,7 @@ def _act_code(activation_fn):
     return None
 
 
-def _fused_dense_bn(x, w2d, bias, scope, bn_decay, is_training, activation_fn):
+def _fused_dense_bn(x, w2d, bias, scope, bn_decay, is_training, activation_fn, fused_kernel=True):
     """conv/fc + bias + batch_norm(train) + activation through the fused pasnl epilogue; None if not applicable
     (CPU tensors, inference mode, exotic activation): the caller then takes the op-by-op path."""
     code = _act_code(activation_fn)
@@ -220,7 +220,7 @@ def _fused_dense_bn(x, w2d, bias, scope, bn_decay, is_training, activation_fn):
         gamma = store.get_variable("gamma", (c,), constant_init(1.0))
         mean = store.get_variable("moving_mean", (c,), constant_init(0.0), trainable=False)
         var = store.get_variable("moving_variance", (c,), constant_init(1.0), trainable=False)
-    return _ops.DenseBNAct.apply(x, w2d, bias, gamma, beta, mean, var, decay, 1e-3, code)
+    return _ops.DenseBNAct.apply(x, w2d, bias, gamma, beta, mean, var, decay, 1e-3, code, fused_kernel)
 
 
 # ---------------------------------------------------------------- batch norm
@@ -238,7 +238,18 @@ def batch_norm_template(inputs, is_training, scope, moments_dims_unused, bn_deca
         mean = store.get_variable("moving_mean", (c,), constant_init(0.0), trainable=False)
         var = store.get_variable("moving_variance", (c,), constant_init(1.0), trainable=False)
     x2 = inputs.reshape(-1, c)
-    y = F.batch_norm(x2, mean, var, gamma, beta, bool(is_training), 1.0 - decay, 1e-3)
+    if not bool(is_training):
+        return F.batch_norm(x2, mean, var, gamma, beta, False, 0.0, 1e-3).reshape(inputs.shape)
+    m = x2.mean(dim=0)
+    v = x2.var(dim=0, unbiased=False)
+    y = (x2 - m) * torch.rsqrt(v + 1e-3) * gamma + beta
+    with torch.no_grad():
+        # rank-2 / rank-4 inputs take TF's fused kernel, which feeds the moving variance the Bessel-corrected batch
+        # variance; rank-3 (conv1d) inputs the biased one (tf.contrib.layers.batch_norm, TF 1.13)
+        rows = x2.shape[0]
+        upd = v * (rows / max(rows - 1, 1)) if inputs.dim() in (2, 4) else v
+        mean.mul_(decay).add_((1.0 - decay) * m)
+        var.mul_(decay).add_((1.0 - decay) * upd)
     return y.reshape(inputs.shape)
 
 
@@ -268,7 +279,7 @@ def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="S
         b = store.get_variable("biases", (num_output_channels,), constant_init(0.0))
         w2 = w.view(cin, num_output_channels)   # a view, not w[0]: select_backward is a zero-fill + copy per layer
         if bn:
-            fused = _fused_dense_bn(inputs, w2, b, "bn", bn_decay, is_training, activation_fn)
+            fused = _fused_dense_bn(inputs, w2, b, "bn", bn_decay, is_training, activation_fn, fused_kernel=False)
             if fused is not None:
                 return fused
         out = torch.matmul(inputs, w2) + b

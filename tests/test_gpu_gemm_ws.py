@@ -1,0 +1,69 @@
+"""The TMA-fed, weights-stationary rows GEMM (csrc/gemm_ws.cu: pasnl_gemm_rows_ws) against an fp64 product:
+both weight layouts, the fused column statistics, the operand prologue f(a) = act(a*scale + shift), ragged row counts,
+k / n that are not multiples of the tile, and the routing of pasnl_gemm_rows_tf32x3 onto it."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ws(a, w, w_kn, stats=False, pro=None, act=0, ldc=None):
+    from pointasnl_b200 import _lib, _ops
+    rows, k = a.shape
+    n = w.shape[1] if w_kn else w.shape[0]
+    ldc = ldc or n
+    c = torch.full((rows, ldc), 7.0, device=a.device)
+    st = torch.zeros(2 * n, dtype=torch.float64, device=a.device) if stats else None
+    sc, sh = (pro if pro is not None else (None, None))
+    assert _lib.load().pasnl_gemm_rows_ws_eligible(rows, k, n, a.data_ptr(), a.stride(0)) == 1
+    _lib.call("pasnl_gemm_rows_ws", rows, k, n, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), 1 if w_kn else 0,
+              c.data_ptr(), ldc, _ops._ptr(st), _ops._ptr(sc), _ops._ptr(sh), act, _ops._stream())
+    return c, st
+
+
+@pytest.mark.parametrize("rows,k,n", [(40000, 128, 128), (37888, 64, 64), (50001, 36, 20), (41111, 100, 70),
+                                      (39000, 20, 128), (262144, 128, 128), (38000, 68, 17)])
+@pytest.mark.parametrize("w_kn", [False, True])
+def test_rows_ws_matches_fp64(cuda, rows, k, n, w_kn):
+    torch.manual_seed(rows + k)
+    a = torch.randn(rows, k, device=cuda) * 1.3 + 0.2
+    w = torch.randn(k, n, device=cuda) / k ** 0.5
+    wt = w if w_kn else w.t().contiguous()
+    c, st = run_ws(a, wt, w_kn, stats=True)
+    want = a.double() @ w.double()
+    scale = float(want.abs().max())
+    err = float((c.double() - want).abs().max()) / scale
+    print(f"   rows={rows} k={k} n={n} w_kn={w_kn}: max error {err:.2e} of the largest output")
+    assert err < 5e-6
+    # the statistics are those of the fp32 result the kernel wrote (what the batch-norm pass that follows normalises)
+    cd = c.double()
+    torch.testing.assert_close(st[:n], cd.sum(0), rtol=1e-7, atol=2e-7 * scale * rows ** 0.5)
+    torch.testing.assert_close(st[n:], (cd * cd).sum(0), rtol=2e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_rows_ws_prologue_and_padded_output_pitch(cuda, act):
+    torch.manual_seed(act)
+    rows, k, n = 45000, 96, 72
+    a = torch.randn(rows, k, device=cuda)
+    w = torch.randn(k, n, device=cuda) / k ** 0.5
+    sc, sh = torch.rand(k, device=cuda) + 0.5, torch.randn(k, device=cuda) * 0.3
+    sc[::5] *= -1.0                                    # negative batch-norm scales happen
+    c, _ = run_ws(a, w, True, pro=(sc, sh), act=act, ldc=80)
+    z = a.double() * sc.double() + sh.double()
+    z = torch.relu(z) if act == 1 else (torch.nn.functional.leaky_relu(z, 0.2) if act == 2 else z)
+    # the kernel rounds z to fp32 (one fma) before splitting it: compare against the fp32-rounded operand
+    want = z.float().double() @ w.double()
+    err = float((c[:, :n].double() - want).abs().max()) / float(want.abs().max())
+    assert err < 5e-6, err
+    assert bool((c[:, n:] == 7.0).all())               # the pitch padding is not touched
+
+
+def test_rows_tf32x3_routes_tall_layers_to_ws_and_both_kernels_agree(cuda, monkeypatch):
+    from pointasnl_b200 import _ops
+    torch.manual_seed(3)
+    a = torch.randn(300000, 64, device=cuda)
+    bt = torch.randn(64, 64, device=cuda) / 8
+    got = _ops.gemm_rows(a, bt)
+    want = a.double() @ bt.double().t()
+    assert float((got.double() - want).abs().max()) / float(want.abs().max()) < 5e-6

@@ -37,7 +37,9 @@ def test_fused_dense_bn_act_forward_backward(cuda, shape, cout, act):
     torch.testing.assert_close(got.detach().cpu().double(), want.detach(), rtol=1e-4, atol=5e-5)
     # moving statistics as TF keeps them: decay*old + (1-decay)*batch, mean includes the conv bias
     torch.testing.assert_close(rmc.cpu().double(), 0.1 * mean.detach(), rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(rvc.cpu().double(), 0.9 + 0.1 * var.detach(), rtol=1e-4, atol=1e-5)
+    # (DenseBNAct's default = TF's fused batch-norm kernel: the moving variance is fed the Bessel-corrected variance)
+    nrows = x.numel() // cin
+    torch.testing.assert_close(rvc.cpu().double(), 0.9 + 0.1 * var.detach() * nrows / (nrows - 1), rtol=1e-4, atol=1e-5)
     g = torch.randn(got.shape)
     want.backward(g.double())
     got.backward(g.to(cuda))

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from bench import make_batch  # noqa: E402
+from bench import WORKLOADS, make_batch  # noqa: E402
 from pointasnl_b200.callers.train_step import TrainStep  # noqa: E402
 
 
@@ -27,11 +27,12 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--torch-profiler", default=None)
     a = ap.parse_args()
-    batch = a.batch or (32 if a.workload == "cls" else 4)
-    points = a.points or (1024 if a.workload == "cls" else 10240)
+    wl = WORKLOADS[a.workload]
+    batch = a.batch or wl["batch"]
+    points = a.points or wl["points"]
     dev = torch.device("cuda:0")
     pc, labels, smpw = make_batch(a.workload, batch, points, 1)
-    ts = TrainStep(a.workload, batch, points, dev, adaptive_sample=a.AS, use_graph=False)
+    ts = TrainStep(wl["model"], batch, points, dev, adaptive_sample=a.AS, use_graph=False, **wl["kw"])
     ts.set_inputs(torch.from_numpy(pc), torch.from_numpy(labels), None if smpw is None else torch.from_numpy(smpw))
     for _ in range(3):
         ts.step()
