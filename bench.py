@@ -443,7 +443,7 @@ def main():
     ts_prof = ts if args.no_graph else None
     if ts_prof is None:
         ts_prof = TrainStep(wl["model"], batch, points, dev, adaptive_sample=args.AS, use_graph=False, seed=0, **wl["kw"])
-        ts_prof.bucket.all_reduce_mean = lambda *a, **k: None   # rank-0 only pass: no collective
+        ts_prof.bucket.all_reduce_sum = lambda *a, **k: None    # rank-0 only pass: no collective
         ts_prof.set_inputs(h_pc, h_lab, h_w)
         for _ in range(2):
             ts_prof.step()

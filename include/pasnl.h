@@ -252,10 +252,28 @@ int pasnl_softmax_ce_bwd(long rows, int c, const float *logits, const long *labe
 /* One Adam step (TF formulation) over a flat parameter buffer with the L2 regulariser folded in: for elements with
  * l2_mask != 0 the gradient gets + l2_coeff * p and *reg_loss (double, may be NULL) += l2_coeff * p^2 / 2 (pre-update
  * values).  g is multiplied by grad_scale first (1/world after a summed all-reduce).  *step (device int64) is the number
- * of steps taken so far; it is incremented on the stream after the update. */
+ * of steps taken so far; it is incremented on the stream after the update, and then (loss_out != NULL)
+ * *loss_out = *loss_in + *reg_loss is published and *reg_loss cleared for the next step. */
 int pasnl_adam_l2(long n, float *p, const float *g, float *m, float *v, const unsigned char *l2_mask, float l2_coeff,
                   float grad_scale, float lr, float beta1, float beta2, float eps, long *step, double *reg_loss,
-                  void *stream);
+                  const float *loss_in, float *loss_out, void *stream);
+
+/* Max over k <= 64 neighbours with a tie mask, and the scatter form of its gradient: grad_x[g,t,c] += grad_out[g,c] /
+ * popcount(mask[g,c]) for t in mask[g,c], IN PLACE into an existing (groups,k,c) gradient (tf.reduce_max's gradient is
+ * split evenly among tied maxima).  pasnl_add_cols: dst[r][0..nc) += src[r][0..nc) -- the gradient of a leading-column
+ * slice (grouped_xyz = new_point[..., :3], utils/pointasnl_util.py:248-249,268) added in place. */
+int pasnl_maxpool_k_mask(long groups, int k, int c, const float *x, float *out, unsigned long long *mask, void *stream);
+int pasnl_maxpool_k_scatter(long groups, int k, int c, const unsigned long long *mask, const float *grad_out,
+                            float *grad_x, void *stream);
+int pasnl_add_cols(long rows, int nc, const float *src, float *dst, long ldd, void *stream);
+/* dst_i (cols_i, rows_i) = src_i (rows_i, cols_i)^T for `count` matrices in one launch; table (device) holds
+ * {src, dst, rows, cols} as 4 int64 per matrix; max_tiles = the largest ceil(rows/32)*ceil(cols/32). */
+int pasnl_transpose_batched(int count, const long *table, int max_tiles, void *stream);
+
+/* out[r][c] = (x ? x[r][c] : 0) + bias[c] (tf.nn.bias_add; x == NULL initialises a skinny-GEMM accumulator with the
+ * bias).  pasnl_col_sum: out[c] = sum_r x[r][c] (the bias gradient). */
+int pasnl_bias_add(long rows, int n, const float *x, const float *bias, float *out, void *stream);
+int pasnl_col_sum(long rows, int n, const float *x, float *out, void *stream);
 
 #ifdef __cplusplus
 }

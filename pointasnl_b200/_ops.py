@@ -426,20 +426,19 @@ class NLCore(torch.autograd.Function):
 
 
 def gemm_wgrad(x, dy):
-    """x (rows, m), dy (rows, n) -> x^T dy (m, n): the weight gradient, on tcgen05 (pasnl_gemm_wgrad_tf32x3) for tall
-    problems, cuBLAS otherwise."""
+    """x (rows, m), dy (rows, n) -> x^T dy (m, n): the weight gradient.  rows <= 64 (fully connected layers: rows = batch
+    size): pasnl_wgrad_skinny; otherwise the tcgen05 kernels behind pasnl_gemm_wgrad_tf32x3 (TMEM-fed / short /
+    narrow-operand variants, chosen by the library)."""
     rows, m = x.shape
     n = dy.shape[1]
-    # operands with a handful of columns (xyz: 3, 6, 9 channels) take the library's fp32 streaming kernel; 17..31
-    # columns would be mostly padding in a 128-wide UMMA tile and stay on cuBLAS
-    narrow = min(m, n) <= 16
-    # (tools/sweep_wgrad_small.py: with the TMEM-fed kernel tcgen05 wins from 2048 rows up, also for wide m)
-    if rows < 2048 or (m < 32 and not narrow) or not x.is_cuda or GEMM_IMPL != "tc":
-        return torch.mm(x.t(), dy)
     if x.stride(1) != 1:
         x = x.contiguous()
     if dy.stride(1) != 1:
         dy = dy.contiguous()
+    if rows <= 64:
+        dw = torch.empty((m, n), device=x.device, dtype=torch.float32)
+        _call("pasnl_wgrad_skinny", rows, m, n, _ptr(x), int(x.stride(0)), _ptr(dy), int(dy.stride(0)), _ptr(dw), n, _stream())
+        return dw
     dw = _zero_arena.zeros((m, n), torch.float32) if (_zero_arena is not None and _zero_arena.device == x.device) else None
     zeroed = dw is not None
     if dw is None:
@@ -523,28 +522,102 @@ def _zeros(shape, dtype, device):
 
 import os as _os
 
-GEMM_MIN_ROWS = 512   # below this a 128-row tile grid cannot fill the GPU: cuBLAS takes those (fc layers, rows = batch)
 GEMM_K_SLAB = 1024
-GEMM_IMPL = _os.environ.get("PASNL_GEMM", "tc")   # "tc" = tcgen05 3xTF32 kernel, "cublas" = torch.mm (fp32 SIMT)
 
 
-def gemm_rows(a, bt, col_stats=None):
-    """a (rows, k) @ bt (n, k)^T -> (rows, n), fp32-accurate, on tcgen05 (pasnl_gemm_rows_tf32x3) when the problem is
-    tall enough, cuBLAS otherwise.  Both operands row-major with a unit inner stride.
-    col_stats: optional zeroed (2n,) float64 tensor; if the tensor-core path runs as a single k slab its epilogue
-    adds the per-column sum / sum of squares of the result into it and the function returns (c, True)."""
+class WeightTransposer:
+    """K-major ([n][k]) copies of the layers' [k][n] weight matrices for the tcgen05 kernels that want them, refreshed
+    for ALL registered weights by ONE pasnl_transpose_batched launch per optimizer step (eager PyTorch: one
+    `w.t().contiguous()` kernel per layer per step).  Weights that are not registered are transposed on demand by a
+    single-matrix launch of the same kernel."""
+
+    def __init__(self):
+        self.by_ptr = {}        # data_ptr of the [k][n] weight -> (k, n, transposed tensor, fresh flag holder)
+        self.table = None
+        self.count = 0
+        self.max_tiles = 1
+        self.managed = False
+
+    def register(self, weights):
+        """weights: list of parameters viewable as (k, n) = (prod(shape[:-1]), shape[-1]); call after the parameters
+        have their final storage (TrainStep: after flatten_parameters)."""
+        weights = list(weights)
+        rows = []
+        for w in weights:
+            n = w.shape[-1]
+            k = w.numel() // n
+            wt = torch.empty((n, k), device=w.device, dtype=torch.float32)
+            self.by_ptr[w.data_ptr()] = (k, n, wt)
+            rows.append([w.data_ptr(), wt.data_ptr(), k, n])
+            self.max_tiles = max(self.max_tiles, ((k + 31) // 32) * ((n + 31) // 32))
+        if rows:
+            self.table = torch.tensor(rows, dtype=torch.int64, device=weights[0].device)
+            self.count = len(rows)
+            self.managed = True
+
+    def refresh(self):
+        if self.count:
+            _call("pasnl_transpose_batched", self.count, _ptr(self.table), int(self.max_tiles), _stream())
+
+    def lookup(self, w2d):
+        hit = self.by_ptr.get(w2d.data_ptr())
+        if hit is not None and hit[0] == w2d.shape[0] and hit[1] == w2d.shape[1]:
+            return hit[2]
+        return None
+
+
+_transposer = None
+_single_tables = {}
+
+
+def set_weight_transposer(t):
+    global _transposer
+    _transposer = t
+
+
+def transposed_weight(w2d):
+    """[n][k] copy of a [k][n] weight: the step's batched refresh if the weight is registered, else one launch now."""
+    if _transposer is not None:
+        wt = _transposer.lookup(w2d)
+        if wt is not None:
+            return wt
+    k, n = w2d.shape
+    if not w2d.is_contiguous():
+        w2d = w2d.contiguous()
+    wt = torch.empty((n, k), device=w2d.device, dtype=torch.float32)
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("weight used inside CUDA-graph capture without a registered WeightTransposer entry")
+    table = torch.tensor([[w2d.data_ptr(), wt.data_ptr(), k, n]], dtype=torch.int64, device=w2d.device)
+    _call("pasnl_transpose_batched", 1, _ptr(table), ((k + 31) // 32) * ((n + 31) // 32), _stream())
+    return wt
+
+
+def gemm_rows(a, w, w_kn=False, col_stats=None):
+    """a (rows, k) times a weight -> (rows, n), fp32-accurate (3xTF32 on tcgen05, fp32 FMA for rows <= 64).
+    w is [n][k] (w_kn=False: the transposed form, e.g. the stored weight seen from the input-gradient product) or [k][n]
+    (w_kn=True: the layer's stored weight).  Routing: rows <= 64 -> pasnl_gemm_skinny; tall layers with k, n <= 128 ->
+    pasnl_gemm_rows_ws (TMA-fed, weights stationary in TMEM; takes either layout); everything else ->
+    pasnl_gemm_rows_tf32x3, which wants [n][k] (a [k][n] weight goes through the step's batched transpose).
+    col_stats: optional zeroed (2n,) float64 tensor; when the kernel's epilogue can accumulate the per-column sum / sum
+    of squares of the result into it the function returns (c, True), else (c, False)."""
     rows, k = a.shape
-    n = bt.shape[0]
-    # measured on B200 (tools/sweep_gemm2.py): the tcgen05 kernel wins whenever there are >= 128 row tiles; with only
-    # 32 row tiles (rows = 4096: the classifier heads) it needs a wide n to fill the GPU, otherwise cuBLAS' split-k wins
-    use_tc = a.is_cuda and GEMM_IMPL == "tc" and rows >= GEMM_MIN_ROWS and (rows >= 16384 or (n >= 512 and k <= 1024))
-    if not use_tc:
-        c = torch.mm(a, bt.t())
-        return c if col_stats is None else (c, False)
+    n = w.shape[1] if w_kn else w.shape[0]
     if a.stride(1) != 1:
         a = a.contiguous()
-    if bt.stride(1) != 1:
-        bt = bt.contiguous()
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    if rows <= 64:
+        c, _ = _zeros((rows, n), torch.float32, a.device)
+        _call("pasnl_gemm_skinny", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(w), int(w.stride(0)), 0 if w_kn else 1,
+              _ptr(c), n, _stream())
+        return c if col_stats is None else (c, False)
+    lib = _lib.load()
+    if lib.pasnl_gemm_rows_ws_eligible(rows, k, n, a.data_ptr(), int(a.stride(0))):
+        c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
+        _call("pasnl_gemm_rows_ws", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(w), int(w.stride(0)), 1 if w_kn else 0,
+              _ptr(c), n, _ptr(col_stats), None, None, 0, _stream())
+        return c if col_stats is None else (c, True)
+    bt = transposed_weight(w) if w_kn else w
     # The TMEM accumulator truncates on every add (error ~3e-8 * k * |C|): long contractions are cut into <= 1024-wide
     # slabs whose partial products are summed with round-to-nearest fp32 adds.  (Long k only occurs with few rows --
     # the PointConv `after_conv`, 2048/4096 wide on 16384/4096 rows -- so the extra pass is tiny, and the slabs give
@@ -557,7 +630,10 @@ def gemm_rows(a, bt, col_stats=None):
         asl, bsl = a[:, k0:k0 + kk], bt[:, k0:k0 + kk]
         _call("pasnl_gemm_rows_tf32x3", rows, kk, n, asl.data_ptr(), int(a.stride(0)), bsl.data_ptr(), int(bt.stride(0)),
               _ptr(c), n, _ptr(col_stats) if fuse_stats else None, _stream())
-        out = c if out is None else out.add_(c)
+        if out is None:
+            out = c
+        else:
+            _call("pasnl_add_n", out.numel(), _ptr(out), _ptr(c), None, _ptr(out), _stream())
     return out if col_stats is None else (out, fuse_stats)
 
 
@@ -567,6 +643,19 @@ def _bn_single_launch(rows, c):
         return False
     lanes = c // 4 if c % 4 == 0 else c
     return rows * c <= (4 << 20) and lanes <= 256
+
+
+def _rows_view(x, cin):
+    """(rows, cin) view of x with a unit channel stride and ONE row pitch (a leading-column slice such as
+    grouped_xyz = new_point[..., :3] qualifies: the GEMM kernels take a row pitch); a contiguous copy otherwise."""
+    if x.dim() >= 2 and x.stride(-1) == 1 and x.shape[-1] == cin:
+        dims = [(x.shape[d], x.stride(d)) for d in range(x.dim() - 1) if x.shape[d] != 1]
+        ok = all(dims[i][1] == dims[i + 1][1] * dims[i + 1][0] for i in range(len(dims) - 1))
+        if ok:
+            pitch = dims[-1][1] if dims else cin
+            if pitch >= cin:
+                return x.as_strided((x.numel() // cin, cin), (pitch, 1))
+    return x.reshape(-1, cin).contiguous()
 
 
 class DenseBNAct(torch.autograd.Function):
@@ -579,12 +668,10 @@ class DenseBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w2d, bias, gamma, beta, running_mean, running_var, decay, eps, act, unbiased_moving_var=True):
         cin, cout = w2d.shape
-        x2 = x.reshape(-1, cin)
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
+        x2 = _rows_view(x, cin)
         ws, _ = _zeros((2 * cout,), torch.float64, x2.device)
         # x.W on tensor cores (3xTF32); the GEMM epilogue also accumulates the batch-norm statistics when it can
-        y, stats_ready = gemm_rows(x2, w2d.t().contiguous(), col_stats=ws)
+        y, stats_ready = gemm_rows(x2, w2d, w_kn=True, col_stats=ws)
         rows = y.shape[0]
         out = torch.empty_like(y)
         mean = torch.empty((cout,), device=y.device, dtype=torch.float32)
@@ -619,7 +706,228 @@ class DenseBNAct(torch.autograd.Function):
             _lib.launch_count -= 2      # clear + reduce + apply ran as one cooperative launch
         elif ws_zeroed:
             _lib.launch_count -= 1      # no memset node was enqueued
-        dx = gemm_rows(dy, w2d).reshape(xshape) if ctx.needs_input_grad[0] else None   # dy.W^T: Bt = W as stored
+        dx = gemm_rows(dy, w2d, w_kn=False).reshape(xshape) if ctx.needs_input_grad[0] else None   # dy.W^T: [n][k] = W as stored
         dw = gemm_wgrad(x2, dy) if ctx.needs_input_grad[1] else None
         dbias = _zeros(gamma.shape, torch.float32, gamma.device)[0] if ctx.needs_input_grad[2] else None
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------ launch-bound glue (csrc/small_ops.cu)
+class AddN(torch.autograd.Function):
+    """a + b (+ c): the tf.add chains of the layer functions (pointasnl_util.py:283-285) as one kernel."""
+
+    @staticmethod
+    def forward(ctx, a, b, c=None):
+        a, b = _f32(a, "a"), _f32(b, "b")
+        _require(a.shape == b.shape and (c is None or c.shape == a.shape), "add_n expects equal shapes")
+        c = _f32(c, "c") if c is not None else None
+        out = torch.empty_like(a)
+        _call("pasnl_add_n", a.numel(), _ptr(a), _ptr(b), _ptr(c), _ptr(out), _stream())
+        ctx.has_c = c is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g, (g if ctx.has_c else None)
+
+
+def add_n(a, b, c=None):
+    if a.is_cuda:
+        return AddN.apply(a, b, c)
+    return a + b if c is None else a + b + c
+
+
+class ConcatCols(torch.autograd.Function):
+    """torch.cat([a, b], dim=-1) for tensors with equal leading shapes (tf.concat(axis=-1))."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _f32(a, "a"), _f32(b, "b")
+        _require(a.shape[:-1] == b.shape[:-1], "concat_cols expects equal leading shapes")
+        ca, cb = a.shape[-1], b.shape[-1]
+        rows = a.numel() // ca
+        out = torch.empty(a.shape[:-1] + (ca + cb,), device=a.device, dtype=torch.float32)
+        _call("pasnl_concat_cols", rows, ca, cb, _ptr(a), ca, _ptr(b), cb, _ptr(out), _stream())
+        ctx.dims = (rows, ca, cb, a.shape, b.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, ca, cb, sa, sb = ctx.dims
+        g = _f32(g, "grad")
+        ga = torch.empty(sa, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        gb = torch.empty(sb, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        _call("pasnl_split_cols", rows, ca, cb, _ptr(g), _ptr(ga), _ptr(gb), _stream())
+        return ga, gb
+
+
+def concat_cols(a, b):
+    if a.is_cuda:
+        return ConcatCols.apply(a, b)
+    return torch.cat([a, b], dim=-1)
+
+
+def split_cols(x, ca):
+    """x (..., ca+cb) -> contiguous (..., ca), (..., cb) copies (tf.slice of the input placeholder); no gradient."""
+    x = _f32(x.detach(), "x")
+    w = x.shape[-1]
+    cb = w - ca
+    rows = x.numel() // w
+    a = torch.empty(x.shape[:-1] + (ca,), device=x.device, dtype=torch.float32)
+    b = torch.empty(x.shape[:-1] + (cb,), device=x.device, dtype=torch.float32)
+    _call("pasnl_split_cols", rows, ca, cb, _ptr(x), _ptr(a), _ptr(b), _stream())
+    return a, b
+
+
+_dropout_step = None     # device int64 scalar: the optimizer's step counter (set by TrainStep) -> fresh masks per replay
+_dropout_calls = 0
+
+
+def set_dropout_step(t):
+    global _dropout_step
+    _dropout_step = t
+
+
+class Dropout(torch.autograd.Function):
+    """tf.nn.dropout(x, keep_prob): the mask is a counter-based function of (seed, step, index), regenerated in the
+    backward pass instead of being stored."""
+
+    @staticmethod
+    def forward(ctx, x, keep_prob, seed):
+        x = _f32(x, "x")
+        out = torch.empty_like(x)
+        _call("pasnl_dropout", x.numel(), _ptr(x), float(keep_prob), int(seed), _ptr(_dropout_step), _ptr(out), _stream())
+        ctx.args = (float(keep_prob), int(seed), _dropout_step)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        keep, seed, step = ctx.args
+        g = _f32(g, "grad")
+        out = torch.empty_like(g)
+        _call("pasnl_dropout", g.numel(), _ptr(g), keep, seed, _ptr(step), _ptr(out), _stream())
+        return out, None, None
+
+
+def dropout(x, keep_prob, seed):
+    return Dropout.apply(x, keep_prob, seed)
+
+
+class SoftmaxCE(torch.autograd.Function):
+    """Sparse soft-max cross entropy -> scalar.  weights None: out_scale * mean (pointasnl_cls.py:60-61); else
+    out_scale * sum(w * ce) / max(count_nonzero(w), 1) (tf.losses.sparse_softmax_cross_entropy, sem_seg_res.py:81)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weights, out_scale):
+        logits = _f32(logits, "logits")
+        c = logits.shape[-1]
+        rows = logits.numel() // c
+        _require(labels.is_cuda and labels.dtype == torch.int64 and labels.numel() == rows, "labels must be CUDA int64 (rows,)")
+        labels = labels.contiguous()
+        weights = _f32(weights, "weights") if weights is not None else None
+        lse = torch.empty((rows,), device=logits.device, dtype=torch.float32)
+        ws = torch.empty((4,), device=logits.device, dtype=torch.float64)
+        loss = torch.empty((), device=logits.device, dtype=torch.float32)
+        _call("pasnl_softmax_ce_fwd", rows, c, _ptr(logits), _ptr(labels), _ptr(weights), float(out_scale), _ptr(lse),
+              _ptr(ws), _ptr(loss), _stream())
+        ctx.save_for_backward(logits, labels, weights, lse, ws)
+        ctx.out_scale = float(out_scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, weights, lse, ws = ctx.saved_tensors
+        c = logits.shape[-1]
+        rows = logits.numel() // c
+        g = _f32(g, "grad").reshape(())
+        d = torch.empty_like(logits)
+        _call("pasnl_softmax_ce_bwd", rows, c, _ptr(logits), _ptr(labels), _ptr(weights), ctx.out_scale, _ptr(lse), _ptr(ws),
+              _ptr(g), _ptr(d), _stream())
+        return d, None, None, None
+
+
+def softmax_ce(logits, labels, weights=None, out_scale=1.0):
+    return SoftmaxCE.apply(logits, labels, weights, out_scale)
+
+
+class DenseBias(torch.autograd.Function):
+    """x @ w + bias for a layer without batch norm (tf_util.fully_connected / conv1d with bn=False: the logits layers)."""
+
+    @staticmethod
+    def forward(ctx, x, w2d, bias):
+        cin, cout = w2d.shape
+        x2 = _rows_view(_f32(x, "x"), cin)
+        rows = x2.shape[0]
+        if rows <= 64:          # bias-initialised accumulator, then the split-k skinny GEMM adds into it
+            out = torch.empty((rows, cout), device=x.device, dtype=torch.float32)
+            _call("pasnl_bias_add", rows, cout, None, _ptr(bias), _ptr(out), _stream())
+            w = w2d if w2d.stride(1) == 1 else w2d.contiguous()
+            _call("pasnl_gemm_skinny", rows, cin, cout, _ptr(x2), int(x2.stride(0)), _ptr(w), int(w.stride(0)), 0,
+                  _ptr(out), cout, _stream())
+        else:
+            y = gemm_rows(x2, w2d, w_kn=True)
+            out = torch.empty_like(y)
+            _call("pasnl_bias_add", rows, cout, _ptr(y), _ptr(bias), _ptr(out), _stream())
+        ctx.save_for_backward(x2, w2d)
+        ctx.xshape = x.shape
+        return out.reshape(x.shape[:-1] + (cout,))
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w2d = ctx.saved_tensors
+        cin, cout = w2d.shape
+        g2 = _f32(g, "grad").reshape(-1, cout)
+        dx = gemm_rows(g2, w2d, w_kn=False).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = gemm_wgrad(x2, g2) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.needs_input_grad[2]:
+            db = torch.empty((cout,), device=g2.device, dtype=torch.float32)
+            _call("pasnl_col_sum", g2.shape[0], cout, _ptr(g2), _ptr(db), _stream())
+        return dx, dw, db
+
+
+class SAFront(torch.autograd.Function):
+    """The three readers of the grouped tensor new_point (B, S, K, W) = [xyz_j - centre | xyz_j | feature_j] in one
+    autograd node (utils/pointasnl_util.py:258,264-268): the skip connection's max over the K neighbours, the identity
+    that feeds conv0, and the grouped_xyz = new_point[..., :3] slice that feeds the weight net.
+    Backward: the dense gradient arriving through the identity output (conv0's input gradient) is taken as the result
+    buffer; the max-pool gradient is SCATTERED into it through the tie mask saved by the forward pass and the 3-column
+    slice gradient is added in place -- instead of a dense (B,S,K,W) max-pool gradient, a zero-filled slice gradient
+    and two full-tensor adds (cls layer 2: five extra passes over a 140 MB tensor)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x, "new_point")
+        b, s, k, w = x.shape
+        _require(k <= 64, "SAFront supports up to 64 neighbours")
+        pooled = torch.empty((b, s, w), device=x.device, dtype=torch.float32)
+        mask = torch.empty((b, s, w), device=x.device, dtype=torch.int64)
+        _call("pasnl_maxpool_k_mask", b * s, k, w, _ptr(x), _ptr(pooled), _ptr(mask), _stream())
+        xyz = torch.empty((b, s, k, 3), device=x.device, dtype=torch.float32)
+        _call("pasnl_split_cols", b * s * k, 3, w - 3, _ptr(x), _ptr(xyz), None, _stream())
+        ctx.save_for_backward(mask)
+        ctx.dims = (b, s, k, w)
+        ident = x.view_as(x)
+        return pooled, ident, xyz
+
+    @staticmethod
+    def backward(ctx, g_pooled, g_ident, g_xyz):
+        (mask,) = ctx.saved_tensors
+        b, s, k, w = ctx.dims
+        if g_ident is None:
+            g = torch.zeros((b, s, k, w), device=mask.device, dtype=torch.float32)
+        else:
+            g = _f32(g_ident, "grad")          # owned by this node: the only consumer of `ident` is conv0
+        if g_pooled is not None:
+            _call("pasnl_maxpool_k_scatter", b * s, k, w, _ptr(mask), _ptr(_f32(g_pooled, "grad")), _ptr(g), _stream())
+        if g_xyz is not None:
+            _call("pasnl_add_cols", b * s * k, 3, _ptr(_f32(g_xyz, "grad")), _ptr(g), w, _stream())
+        return g
+
+
+def adam_l2(flat_p, flat_g, m, v, l2_mask, l2_coeff, grad_scale, lr, step, reg_loss, loss_in=None, loss_out=None,
+            beta1=0.9, beta2=0.999, eps=1e-8):
+    """One TF-style Adam step with the L2 regulariser folded in (pasnl_adam_l2); publishes loss_out = loss_in + reg."""
+    _call("pasnl_adam_l2", flat_p.numel(), _ptr(flat_p), _ptr(flat_g), _ptr(m), _ptr(v), _ptr(l2_mask), float(l2_coeff),
+          float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), _ptr(step), _ptr(reg_loss), _ptr(loss_in),
+          _ptr(loss_out), _stream())

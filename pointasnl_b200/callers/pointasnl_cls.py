@@ -4,7 +4,7 @@ the reference's scope names (layer1/..., layer2/..., layer3_1, layer3_2, fc1, fc
 import torch
 import torch.nn.functional as F
 
-from .. import tf_util
+from .. import _ops, tf_util
 from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss
 from ..pointnet_util import pointnet_sa_module
 
@@ -26,7 +26,9 @@ def get_model(point_cloud, is_training, use_normal=False, bn_decay=None, weight_
     """point_cloud (B, N, 3 or 6) -> logits (B, num_class), end_points."""
     batch_size = point_cloud.shape[0]
     end_points = {}
-    if use_normal:
+    if use_normal and point_cloud.is_cuda:
+        xyz, points = _ops.split_cols(point_cloud, 3)
+    elif use_normal:
         xyz, points = point_cloud[:, :, 0:3].contiguous(), point_cloud[:, :, 3:6].contiguous()
     else:
         xyz = points = point_cloud
@@ -47,7 +49,7 @@ def get_model(point_cloud, is_training, use_normal=False, bn_decay=None, weight_
         _, feat, _ = pointnet_sa_module(lx, lp, npoint=None, radius=None, nsample=None, mlp=mlp, mlp2=None,
                                         group_all=True, is_training=is_training, bn_decay=bn_decay, scope=scope)
         pooled.append(feat.reshape(batch_size, -1))
-    net = torch.cat([pooled[1], pooled[0]], dim=-1)       # [l3_points, l3_points_res] (:45)
+    net = _ops.concat_cols(pooled[1], pooled[0])          # [l3_points, l3_points_res] (:45)
     net = tf_util.fully_connected(net, 512, bn=True, is_training=is_training, scope="fc1", bn_decay=bn_decay)
     net = tf_util.dropout(net, keep_prob=0.4, is_training=is_training, scope="dp1")
     net = tf_util.fully_connected(net, 256, bn=True, is_training=is_training, scope="fc2", bn_decay=bn_decay)
@@ -64,10 +66,10 @@ def l2_on_weights(store):
 def get_loss(pred, label, end_points, uniform_weight=0, weights_decay=1e-4):
     """pred (B, num_class), label (B,) -> total loss (:55-70)."""
     store = tf_util.get_default_store()
-    regularization_loss = weights_decay * l2_on_weights(store)
-    classify_loss = F.cross_entropy(pred, label)
+    classify_loss = _ops.softmax_ce(pred, label) if pred.is_cuda else F.cross_entropy(pred, label)
+    total = classify_loss
     if uniform_weight > 0:
-        uniform_loss = get_repulsion_loss(end_points["l1_xyz"], nsample=20, radius=0.07)
-    else:
-        uniform_loss = classify_loss
-    return classify_loss + uniform_weight * uniform_loss + regularization_loss
+        total = total + uniform_weight * get_repulsion_loss(end_points["l1_xyz"], nsample=20, radius=0.07)
+    if weights_decay:       # weights_decay=0: the caller folds the regulariser into its optimizer kernel (TrainStep)
+        total = total + weights_decay * l2_on_weights(store)
+    return total

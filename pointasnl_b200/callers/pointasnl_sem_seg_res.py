@@ -3,7 +3,7 @@
 import torch
 import torch.nn.functional as F
 
-from .. import tf_util
+from .. import _ops, tf_util
 from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss, index_cache
 from ..pointnet_util import pointnet_fp_module
 from .pointasnl_cls import l2_on_weights
@@ -30,7 +30,9 @@ def get_model(point_cloud, is_training, num_class, bn_decay=None, weight_decay=N
 def _get_model(point_cloud, is_training, num_class, bn_decay, weight_decay, feature_channel):
     end_points = {}
     num_point = point_cloud.shape[1]
-    if feature_channel > 0:
+    if feature_channel > 0 and point_cloud.is_cuda and point_cloud.shape[2] == 3 + feature_channel:
+        l0_xyz, l0_points = _ops.split_cols(point_cloud, 3)
+    elif feature_channel > 0:
         l0_xyz = point_cloud[:, :, 0:3].contiguous()
         l0_points = point_cloud[:, :, 3:3 + feature_channel].contiguous()
     else:
@@ -43,16 +45,16 @@ def _get_model(point_cloud, is_training, num_class, bn_decay, weight_decay, feat
     # each residual stage: a sampling layer (FPS + AS + NL) and a same-resolution refinement layer, summed
     l1_xyz, l1_1 = _sa(l0_xyz, l0_points, n1, [32, 32, 64], "layer1_1", 8, True, cfg)
     _, l1_2 = _sa(l0_xyz, l0_points, n1, [64, 64], "layer1_2", 0, False, cfg)
-    l1_2 = l1_2 + l1_1
+    l1_2 = _ops.add_n(l1_2, l1_1)
     l2_xyz, l2_1 = _sa(l1_xyz, l1_2, n2, [64, 64, 128], "layer2_1", 4, True, cfg)
     _, l2_2 = _sa(l2_xyz, l2_1, n2, [128, 128], "layer2_2", 0, False, cfg)
-    l2_2 = l2_2 + l2_1
+    l2_2 = _ops.add_n(l2_2, l2_1)
     l3_xyz, l3_1 = _sa(l2_xyz, l2_2, n3, [128, 128, 256], "layer3_1", 0, True, cfg)
     _, l3_2 = _sa(l3_xyz, l3_1, n3, [256, 256], "layer3_2", 0, False, cfg)
-    l3_2 = l3_2 + l3_1
+    l3_2 = _ops.add_n(l3_2, l3_1)
     l4_xyz, l4_1 = _sa(l3_xyz, l3_1, n4, [256, 256, 512], "layer4_1", 0, True, cfg)   # sic: consumes l3_1 (:50)
     _, l4_2 = _sa(l4_xyz, l4_1, n4, [512, 512], "layer4_2", 0, False, cfg)
-    l4_2 = l4_2 + l4_1
+    l4_2 = _ops.add_n(l4_2, l4_1)
     end_points["l1_xyz"] = l1_xyz
 
     l3_points = pointnet_fp_module(l3_xyz, l4_xyz, l3_2, l4_2, [512, 512], is_training, bn_decay, scope="fa_layer1")
@@ -73,13 +75,16 @@ def get_loss(pred, label, end_points, smpw=1.0, uniform_weight=0.01, weights_dec
     """pred (B, N, C), label (B, N), smpw (B, N) -> total loss (:72-88).  tf.losses.sparse_softmax_cross_entropy with
     weights = weighted sum / number of non-zero weights."""
     store = tf_util.get_default_store()
-    regularization_loss = weights_decay * l2_on_weights(store)
-    ce = F.cross_entropy(pred.reshape(-1, pred.shape[-1]), label.reshape(-1), reduction="none")
-    if torch.is_tensor(smpw):
-        w = smpw.reshape(-1)
-        classify_loss = (ce * w).sum() / torch.count_nonzero(w).clamp(min=1)
+    if pred.is_cuda and torch.is_tensor(smpw):
+        classify_x2 = _ops.softmax_ce(pred, label, smpw, out_scale=2.0)    # see below: the reference counts it twice
     else:
-        classify_loss = (ce * smpw).mean()
+        ce = F.cross_entropy(pred.reshape(-1, pred.shape[-1]), label.reshape(-1), reduction="none")
+        if torch.is_tensor(smpw):
+            w = smpw.reshape(-1)
+            classify_loss = (ce * w).sum() / torch.count_nonzero(w).clamp(min=1)
+        else:
+            classify_loss = (ce * smpw).mean()
+        classify_x2 = 2.0 * classify_loss
     uniform_loss = get_repulsion_loss(end_points["l1_xyz"], nsample=20, radius=radius)
     # :83 `weight_reg = tf.add_n(tf.get_collection('losses'))`.  tf.losses.sparse_softmax_cross_entropy registers its
     # result in that very collection (loss_collection=GraphKeys.LOSSES), next to the per-variable weight-decay terms
@@ -87,5 +92,9 @@ def get_loss(pred, label, end_points, smpw=1.0, uniform_weight=0.01, weights_dec
     # counts the classification loss TWICE.  (Every reference training script leaves weight_decay=None; without the
     # registered classify_loss `tf.add_n([])` would not even build.)  Reproduced, and pinned by
     # tests/golden/tf_graph_seg.npz, which executes the reference's own get_loss.
-    weight_reg = classify_loss + store.regularization_loss()
-    return classify_loss + weight_reg + uniform_weight * uniform_loss + regularization_loss
+    total = classify_x2 + uniform_weight * uniform_loss
+    if store.weight_decay:
+        total = total + store.regularization_loss()
+    if weights_decay:       # weights_decay=0: the caller folds the regulariser into its optimizer kernel (TrainStep)
+        total = total + weights_decay * l2_on_weights(store)
+    return total

@@ -15,6 +15,8 @@ class TrainStep:
         SemanticKITTI/train_semantic_kitti.py:81, train_semantic_kitti_grid.py:144)."""
         self.kind = model
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("TrainStep drives the CUDA library (optimizer kernel included): it needs a CUDA device")
         self.batch_size, self.num_point = batch_size, num_point
         self.adaptive_sample = adaptive_sample
         self.feature_channel = feature_channel
@@ -36,43 +38,83 @@ class TrainStep:
         with torch.no_grad():
             self._forward(is_training=False)
         self.bucket = FlatGradBucket(self.store.parameters())
-        # Adam over ONE flat parameter (all variables are views of it, its .grad is the gradient bucket): a single fused
-        # kernel per step (per-tensor multi-tensor launches: 0.12 ms; the foreach implementation: ~60 kernels, 0.95 ms)
+        # ONE flat parameter buffer (all variables are views of it; the gradient bucket mirrors its layout) updated by ONE
+        # library kernel per step: L2 regulariser on the 'weights' variables + TF-style Adam (pasnl_adam_l2).
         self.flat_param = self.bucket.flatten_parameters()
-        self.opt = torch.optim.Adam([self.flat_param], lr=lr, capturable=use_graph, fused=True)
-        # zero-initialised scratch of the dense glue, cleared once per step instead of ~100 separate fill nodes
+        self.lr = float(lr)
+        self.l2_coeff = 1e-4                       # get_loss(weights_decay=1e-4) of both reference models
+        dev = self.device
+        self.adam_m = torch.zeros_like(self.flat_param.data)
+        self.adam_v = torch.zeros_like(self.flat_param.data)
+        self.adam_step = torch.zeros((), dtype=torch.int64, device=dev)
+        self.reg_loss = torch.zeros((), dtype=torch.float64, device=dev)
+        self.l2_mask = torch.zeros(self.flat_param.numel(), dtype=torch.uint8, device=dev)
+        by_param = {id(v): name for name, v in self.store.variables().items()}
+        off = 0
+        weight_params = []
+        for prm in self.bucket.params:
+            name = by_param.get(id(prm), "")
+            if "weights" in name:                  # tf.global_variables() with 'weights' in the name (pointasnl_cls.py:58)
+                self.l2_mask[off:off + prm.numel()] = 1
+                if prm.dim() >= 2:
+                    weight_params.append(prm)
+            off += prm.numel()
         from .. import _ops
+        # zero-initialised scratch of the dense glue, cleared once per step instead of ~100 separate fill nodes
         self.arena = _ops.ZeroArena(self.device) if self.device.type == "cuda" else None
+        # K-major copies of every weight matrix, refreshed by one batched launch at the start of a step
+        self.transposer = None
+        if self.device.type == "cuda":
+            self.transposer = _ops.WeightTransposer()
+            self.transposer.register(weight_params)
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None
 
-    def _forward(self, is_training=True):
+    def _forward(self, is_training=True, weights_decay=1e-4):
         with self.store.as_default():
             if self.kind == "cls":
                 pred, end_points = pointasnl_cls.get_model(self.points, is_training, use_normal=True,
                                                            adaptive_sample=self.adaptive_sample,
                                                            num_class=self.num_class)
-                return pointasnl_cls.get_loss(pred, self.labels, end_points)
+                return pointasnl_cls.get_loss(pred, self.labels, end_points, weights_decay=weights_decay)
             pred, end_points = pointasnl_sem_seg_res.get_model(self.points, is_training, self.num_class,
                                                                feature_channel=self.feature_channel)
-            return pointasnl_sem_seg_res.get_loss(pred, self.labels, end_points, self.smpw, radius=self.radius)
+            return pointasnl_sem_seg_res.get_loss(pred, self.labels, end_points, self.smpw, radius=self.radius,
+                                                  weights_decay=weights_decay)
 
     def _fwd_bwd(self):
         from .. import _ops
         self.bucket.detach()
         if self.arena is not None:
             self.arena.reset()
-        with _ops.use_zero_arena(self.arena):
-            loss = self._forward()
-            loss.backward()
+        prev_t, prev_d = _ops._transposer, _ops._dropout_step
+        _ops.set_weight_transposer(self.transposer)
+        _ops.set_dropout_step(self.adam_step)
+        try:
+            if self.transposer is not None:
+                self.transposer.refresh()
+            with _ops.use_zero_arena(self.arena):
+                loss = self._forward(weights_decay=0.0)      # the regulariser is folded into the optimizer kernel
+                loss.backward()
+        finally:
+            _ops.set_weight_transposer(prev_t)
+            _ops.set_dropout_step(prev_d)
         self.bucket.pack()
-        self.loss.copy_(loss.detach())
+        self.data_loss = loss.detach()
+
+    def _optimizer_step(self):
+        """L2 + Adam over the flat buffers; also publishes loss = data loss + regulariser and bumps the step counter."""
+        import torch.distributed as dist
+        from .. import _ops
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        _ops.adam_l2(self.flat_param.data, self.bucket.flat, self.adam_m, self.adam_v, self.l2_mask, self.l2_coeff,
+                     1.0 / world, self.lr, self.adam_step, self.reg_loss, self.data_loss, self.loss)
 
     def _eager_step(self):
         self._fwd_bwd()
-        self.bucket.all_reduce_mean()
-        self.opt.step()
+        self.bucket.all_reduce_sum()
+        self._optimizer_step()
 
     def capture(self, warmup=3):
         """Capture fwd+bwd and the optimizer step as two graphs around the (uncaptured) NCCL all-reduce."""
@@ -91,7 +133,7 @@ class TrainStep:
         self.launches_per_step = _lib.launch_count - c0   # pasnl kernels captured in (and replayed by) one step
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt):
-            self.opt.step()
+            self._optimizer_step()
         self.graph = True
 
     def set_inputs(self, points, labels, smpw=None, non_blocking=True):
@@ -104,7 +146,7 @@ class TrainStep:
     def step(self):
         if self.graph:
             self.g_fb.replay()
-            self.bucket.all_reduce_mean()
+            self.bucket.all_reduce_sum()
             self.g_opt.replay()
         else:
             self._eager_step()

@@ -269,7 +269,118 @@ __global__ void adam_l2_kernel(long n, float *__restrict__ p, const float *__res
         }
     }
 }
-__global__ void bump_step_kernel(long *step) { *step += 1; }
+// after the update: step += 1; total loss = data loss + regulariser; the regulariser accumulator is cleared for the next step
+__global__ void bump_step_kernel(long *step, double *reg, const float *loss_in, float *loss_out) {
+    *step += 1;
+    if (loss_out) *loss_out = (loss_in ? *loss_in : 0.f) + (reg ? (float)*reg : 0.f);
+    if (reg) *reg = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ SA-layer front end
+// out[g, c] = max_t x[g, t, c] for k <= 64 neighbours, plus a 64-bit mask of the positions that attain the maximum
+// (ties included: TF's reduce_max gradient is split evenly among them).  With the mask the backward pass is a SCATTER
+// of groups*c values into an existing gradient buffer instead of a dense (groups, k, c) tensor that autograd would
+// then have to add to the other gradients of the same activation (three 140 MB passes on cls layer 2).
+__global__ void __launch_bounds__(256) maxpool_k_mask_kernel(long gc, int k, int c, const float *__restrict__ x,
+                                                             float *__restrict__ out,
+                                                             unsigned long long *__restrict__ mask) {
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < gc; e += (long)gridDim.x * 256) {
+        const long g = e / c;
+        const int ch = (int)(e - g * c);
+        const float *p = x + g * (long)k * c + ch;
+        float m = __ldg(p);
+        unsigned long long bits = 1ull;
+        for (int t = 1; t < k; ++t) {
+            const float v = __ldg(p + (long)t * c);
+            if (v > m) { m = v; bits = 1ull << t; }
+            else if (v == m) bits |= 1ull << t;
+        }
+        out[e] = m;
+        mask[e] = bits;
+    }
+}
+// grad_x[g, t, c] += grad_out[g, c] / popcount(mask[g, c]) for every t in the mask (in place)
+__global__ void __launch_bounds__(256) maxpool_k_scatter_kernel(long gc, int k, int c,
+                                                                const unsigned long long *__restrict__ mask,
+                                                                const float *__restrict__ grad_out,
+                                                                float *__restrict__ grad_x) {
+    for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < gc; e += (long)gridDim.x * 256) {
+        const long g = e / c;
+        const int ch = (int)(e - g * c);
+        unsigned long long bits = __ldg(mask + e);
+        const float share = __ldg(grad_out + e) / (float)__popcll(bits);
+        float *q = grad_x + g * (long)k * c + ch;
+        while (bits) {
+            const int t = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            q[(long)t * c] += share;
+        }
+    }
+}
+// dst[r][0..nc) += src[r][0..nc)  (dst row pitch ldd): the gradient of a leading-column slice, added in place
+__global__ void add_cols_kernel(long rows, int nc, const float *__restrict__ src, float *__restrict__ dst, long ldd) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * nc) return;
+    const long r = e / nc;
+    const int c = (int)(e - r * nc);
+    dst[r * ldd + c] += __ldg(src + e);
+}
+
+// ------------------------------------------------------------------------------------------------ weight transposes
+// table[4*i .. 4*i+3] = {src pointer, dst pointer, rows, cols} of matrix i: dst (cols, rows) = src (rows, cols)^T.
+// One launch refreshes the K-major copies of EVERY layer's weights after an optimizer step (blockIdx.y = matrix).
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const long *__restrict__ table) {
+    __shared__ float tile[32][33];
+    const long *e = table + 4 * (long)blockIdx.y;
+    const float *src = reinterpret_cast<const float *>(e[0]);
+    float *dst = reinterpret_cast<float *>(e[1]);
+    const int rows = (int)e[2], cols = (int)e[3];
+    const int tc = (cols + 31) / 32, tr = (rows + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int tI = blockIdx.x; tI < tc * tr; tI += gridDim.x) {
+        const int r0 = (tI / tc) * 32, c0 = (tI % tc) * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + ty + 8 * j, cc = c0 + tx;
+            tile[ty + 8 * j][tx] = (r < rows && cc < cols) ? __ldg(src + (long)r * cols + cc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cc = c0 + ty + 8 * j, r = r0 + tx;
+            if (cc < cols && r < rows) dst[(long)cc * rows + r] = tile[tx][ty + 8 * j];
+        }
+        __syncthreads();
+    }
+}
+
+// out[r][c] = (x ? x[r][c] : 0) + bias[c]   (tf.nn.bias_add; also the bias-initialised accumulator of a skinny GEMM)
+__global__ void bias_add_kernel(long rows, int n, const float *__restrict__ x, const float *__restrict__ bias,
+                                float *__restrict__ out) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * n) return;
+    const int c = (int)(e % n);
+    out[e] = (x ? __ldg(x + e) : 0.f) + __ldg(bias + c);
+}
+// out[c] += sum_r x[r][c]  (the bias gradient); out zero-initialised by the launcher
+__global__ void __launch_bounds__(256) col_sum_kernel(long rows, int n, const float *__restrict__ x, float *__restrict__ out) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    const long chunk = (rows + gridDim.y - 1) / gridDim.y;
+    const long r0 = (long)blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+    float s = 0.f;
+    if (c < n)
+        for (long r = r0 + ry; r < r1; r += 8) s += __ldg(x + r * n + c);
+    __shared__ float red[8][33];
+    red[ry][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ry == 0 && c < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+        atomicAdd(out + c, t);
+    }
+}
 
 }  // namespace sops
 
@@ -365,11 +476,69 @@ extern "C" int pasnl_softmax_ce_bwd(long rows, int c, const float *logits, const
 
 extern "C" int pasnl_adam_l2(long n, float *p, const float *g, float *m, float *v, const unsigned char *l2_mask,
                              float l2_coeff, float grad_scale, float lr, float beta1, float beta2, float eps, long *step,
-                             double *reg_loss, void *stream) {
+                             double *reg_loss, const float *loss_in, float *loss_out, void *stream) {
     PASNL_CHECK_ARG(n >= 1 && p && g && m && v && step);
     cudaStream_t st = (cudaStream_t)stream;
     sops::adam_l2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, p, g, m, v, l2_mask, l2_coeff, grad_scale, lr, beta1,
                                                                       beta2, eps, step, reg_loss);
-    sops::bump_step_kernel<<<1, 1, 0, st>>>(step);
+    sops::bump_step_kernel<<<1, 1, 0, st>>>(step, reg_loss, loss_in, loss_out);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_maxpool_k_mask(long groups, int k, int c, const float *x, float *out, unsigned long long *mask,
+                                    void *stream) {
+    PASNL_CHECK_ARG(groups >= 0 && k >= 1 && k <= 64 && c >= 1 && (groups == 0 || (x && out && mask)));
+    if (groups == 0) return PASNL_OK;
+    long blocks = (groups * c + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    sops::maxpool_k_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(groups * c, k, c, x, out, mask);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_maxpool_k_scatter(long groups, int k, int c, const unsigned long long *mask, const float *grad_out,
+                                       float *grad_x, void *stream) {
+    PASNL_CHECK_ARG(groups >= 0 && k >= 1 && k <= 64 && c >= 1 && (groups == 0 || (mask && grad_out && grad_x)));
+    if (groups == 0) return PASNL_OK;
+    long blocks = (groups * c + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    sops::maxpool_k_scatter_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(groups * c, k, c, mask, grad_out, grad_x);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_add_cols(long rows, int nc, const float *src, float *dst, long ldd, void *stream) {
+    PASNL_CHECK_ARG(rows >= 0 && nc >= 1 && ldd >= nc && (rows == 0 || (src && dst)));
+    if (rows == 0) return PASNL_OK;
+    const long tot = rows * nc;
+    sops::add_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, nc, src, dst, ldd);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_transpose_batched(int count, const long *table, int max_tiles, void *stream) {
+    PASNL_CHECK_ARG(count >= 0 && (count == 0 || table) && max_tiles >= 1);
+    if (count == 0) return PASNL_OK;
+    const dim3 grid((unsigned)(max_tiles < 64 ? max_tiles : 64), (unsigned)count);
+    sops::transpose_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_bias_add(long rows, int n, const float *x, const float *bias, float *out, void *stream) {
+    PASNL_CHECK_ARG(rows >= 0 && n >= 1 && (rows == 0 || (bias && out)));
+    if (rows == 0) return PASNL_OK;
+    const long tot = rows * n;
+    sops::bias_add_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, n, x, bias, out);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_col_sum(long rows, int n, const float *x, float *out, void *stream) {
+    PASNL_CHECK_ARG(rows >= 0 && n >= 1 && out && (rows == 0 || x));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n, st);
+    if (e != cudaSuccess) return (int)e;
+    if (rows == 0) return PASNL_OK;
+    long slabs = rows / 2048;
+    if (slabs < 1) slabs = 1;
+    if (slabs > 256) slabs = 256;
+    const dim3 grid((unsigned)((n + 31) / 32), (unsigned)slabs);
+    sops::col_sum_kernel<<<grid, 256, 0, st>>>(rows, n, x, out);
     return pasnl_launch_status();
 }

@@ -75,6 +75,14 @@ class FlatGradBucket:
         self.flat.div_(world)
         return None
 
+    def all_reduce_sum(self, group=None):
+        """Single collective, sum only: the 1/world factor is folded into the optimizer kernel (pasnl_adam_l2's
+        grad_scale), which saves the separate division pass over the bucket."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return None
+
     def nbytes(self):
         return self.numel * 4
 

@@ -233,14 +233,18 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
                                                     weight_decay, scope, bn)
         # translation normalisation + concat (reference :248-249): [xyz_j - new_xyz | xyz_j | feature_j]
         new_point = _ops.GroupConcat.apply(xyz, feature, idx, new_xyz)
-        grouped_xyz = new_point[..., :3]
+        if nsample <= 64:
+            # one autograd node for the three readers of new_point: skip-connection max-pool, conv0, weight net
+            skip_spatial, new_point, grouped_xyz = _ops.SAFront.apply(new_point)
+        else:
+            skip_spatial = _ops.MaxPoolK.apply(new_point)
+            grouped_xyz = new_point[..., :3]
 
         if NL:                                                             # reference :252-256
             new_nonlocal_point = PointNonLocalCell(feature, new_feature.unsqueeze(1),
                                                    [max(32, num_channel // 2), nl_channel], is_training, bn_decay,
                                                    weight_decay, scope, bn)
         # skip connection (reference :258-262)
-        skip_spatial = _ops.MaxPoolK.apply(new_point)                      # max over the K neighbours, fused fwd/bwd
         skip_spatial = tf_util.conv1d(skip_spatial, mlp[-1], 1, padding="VALID", stride=1, bn=bn,
                                       is_training=is_training, scope="skip", bn_decay=bn_decay,
                                       weight_decay=weight_decay)
@@ -257,9 +261,7 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
                                    bn=bn, is_training=is_training, scope="after_conv", bn_decay=bn_decay,
                                    weight_decay=weight_decay)
         new_point = new_point.squeeze(2)
-        new_point = new_point + skip_spatial
-        if NL:
-            new_point = new_point + new_nonlocal_point
+        new_point = _ops.add_n(new_point, skip_spatial, new_nonlocal_point if NL else None)
         # feature fusion (reference :287-290)
         new_point = tf_util.conv1d(new_point, mlp[-1], 1, padding="VALID", stride=1, bn=bn, is_training=is_training,
                                    scope="aggregation", bn_decay=bn_decay, weight_decay=weight_decay)
@@ -280,7 +282,7 @@ def PointASNLDecodingLayer(xyz1, xyz2, points1, points2, nsample, mlp, is_traini
         if NL:
             new_nonlocal_point = PointNonLocalCell(points1, points2.unsqueeze(1), [max(32, num_channel), num_channel],
                                                    is_training, bn_decay, weight_decay, scope, bn, mode=mode)
-            points2 = points2 + new_nonlocal_point
+            points2 = _ops.add_n(points2, new_nonlocal_point)
         interpolated_points = three_interpolate(points2, idx, weight)
         grouped_xyz, grouped_feature, _ = grouping(interpolated_points, nsample, xyz1, xyz1, use_xyz=use_xyz,
                                                    use_knn=use_knn, radius=radius)
@@ -292,7 +294,7 @@ def PointASNLDecodingLayer(xyz1, xyz2, points1, points2, nsample, mlp, is_traini
                                     bn=bn, is_training=is_training, scope="decode_after_conv", bn_decay=bn_decay,
                                     weight_decay=weight_decay)
         if points1 is not None:
-            new_points1 = torch.cat([new_points, points1.unsqueeze(2)], dim=-1)
+            new_points1 = _ops.concat_cols(new_points, points1.unsqueeze(2))
         else:
             new_points1 = new_points
         for i, num_out_channel in enumerate(mlp):

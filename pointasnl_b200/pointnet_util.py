@@ -4,7 +4,7 @@ pointnet_fp_module.  The multi-scale / radius-grouping variants of PointNet++ ar
  and are not mirrored."""
 import torch
 
-from . import tf_util
+from . import _ops, tf_util
 from .tf_interpolate import three_interpolate, three_nn
 
 
@@ -16,7 +16,7 @@ def sample_and_group_all(xyz, points, use_xyz=True):
     idx = torch.arange(nsample, device=xyz.device, dtype=torch.int32).reshape(1, 1, nsample).repeat(batch_size, 1, 1)
     grouped_xyz = xyz.reshape(batch_size, 1, nsample, 3)
     if points is not None:
-        new_points = torch.cat([xyz, points], dim=2) if use_xyz else points
+        new_points = _ops.concat_cols(xyz, points) if use_xyz else points
         new_points = new_points.unsqueeze(1)
     else:
         new_points = grouped_xyz
@@ -34,7 +34,6 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
         for i, num_out_channel in enumerate(mlp):
             new_points = tf_util.conv2d(new_points, num_out_channel, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
                                         is_training=is_training, scope="conv%d" % i, bn_decay=bn_decay)
-        from . import _ops
         new_points = (_ops.MaxPoolK.apply(new_points) if new_points.is_cuda else new_points.amax(dim=2)).unsqueeze(2)
         if mlp2 is not None:
             for i, num_out_channel in enumerate(mlp2):
@@ -55,7 +54,7 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
         weight = (1.0 / dist) / norm
         interpolated_points = three_interpolate(points2, idx, weight)
         if points1 is not None:
-            new_points1 = torch.cat([interpolated_points, points1], dim=2)
+            new_points1 = _ops.concat_cols(interpolated_points, points1)
         else:
             new_points1 = interpolated_points
         new_points1 = new_points1.unsqueeze(2)

@@ -41,6 +41,7 @@ class VariableStore(torch.nn.Module):
         self.init_fn = init_fn
         self.device = torch.device(device)
         self._scope = []
+        self.seed = int(seed)
         self._gen = torch.Generator(device="cpu")
         self._gen.manual_seed(seed)
         self.weight_decay = {}   # variable name -> wd  (tf.add_to_collection('losses', wd * l2_loss(var)))
@@ -282,9 +283,10 @@ def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="S
             fused = _fused_dense_bn(inputs, w2, b, "bn", bn_decay, is_training, activation_fn, fused_kernel=False)
             if fused is not None:
                 return fused
+        if not bn:
+            return _dense_bias(inputs, w2, b, activation_fn)
         out = torch.matmul(inputs, w2) + b
-        if bn:
-            out = batch_norm_for_conv1d(out, is_training, bn_decay, "bn", data_format)
+        out = batch_norm_for_conv1d(out, is_training, bn_decay, "bn", data_format)
         if activation_fn is not None:
             out = activation_fn(out)
     return out
@@ -315,9 +317,10 @@ def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], paddi
             fused = _fused_dense_bn(x_, w_, bias, "bn", bn_decay, is_training, activation_fn)
             if fused is not None:
                 return fused
+        if not bn:
+            return _dense_bias(x_, w_, bias, activation_fn)
         out = torch.matmul(x_, w_) + bias
-        if bn:
-            out = batch_norm_for_conv2d(out, is_training, bn_decay, "bn", data_format)
+        out = batch_norm_for_conv2d(out, is_training, bn_decay, "bn", data_format)
         if activation_fn is not None:
             out = activation_fn(out)
     return out
@@ -335,16 +338,36 @@ def fully_connected(inputs, num_outputs, scope, use_xavier=True, stddev=1e-3, we
             fused = _fused_dense_bn(inputs, w, b, "bn", bn_decay, is_training, activation_fn)
             if fused is not None:
                 return fused
+        if not bn:
+            return _dense_bias(inputs, w, b, activation_fn)
         out = torch.matmul(inputs, w) + b
-        if bn:
-            out = batch_norm_for_fc(out, is_training, bn_decay, "bn")
+        out = batch_norm_for_fc(out, is_training, bn_decay, "bn")
         if activation_fn is not None:
             out = activation_fn(out)
     return out
 
 
 def dropout(inputs, is_training, scope, keep_prob=0.5, noise_shape=None):
-    """tf.nn.dropout(inputs, keep_prob) when training (reference tf_util.py:590-615)."""
+    """tf.nn.dropout(inputs, keep_prob) when training (reference tf_util.py:590-615).  On CUDA the mask comes from the
+    library's counter-based generator (seeded by the scope name and the store's seed, advanced by the optimizer step)."""
     if noise_shape is not None:
         raise NotImplementedError("noise_shape is not used on the hot path")
-    return F.dropout(inputs, p=1.0 - keep_prob, training=bool(is_training))
+    if not bool(is_training):
+        return inputs
+    if inputs.is_cuda and inputs.dtype == torch.float32:
+        import zlib
+        from . import _ops
+        store = get_default_store()
+        seed = (zlib.crc32(store.full_name(scope).encode()) << 20) ^ int(getattr(store, "seed", 0))
+        return _ops.dropout(inputs, keep_prob, seed)
+    return F.dropout(inputs, p=1.0 - keep_prob, training=True)
+
+
+def _dense_bias(x, w2d, bias, activation_fn):
+    """x @ w + b (+ activation) for a layer without batch norm; the library's GEMMs on CUDA."""
+    if x.is_cuda and x.dtype == torch.float32:
+        from . import _ops
+        out = _ops.DenseBias.apply(x, w2d, bias)
+    else:
+        out = torch.matmul(x, w2d) + bias
+    return activation_fn(out) if activation_fn is not None else out

@@ -58,7 +58,7 @@ def test_tf_util_layers_take_the_fused_path_and_match_op_by_op(cuda):
     with store.as_default():
         c0 = _lib.launch_count
         fused = tf_util.conv2d(x, 24, [1, 1], "c", padding="VALID", bn=True, is_training=True)
-        assert _lib.launch_count - c0 == 2            # tcgen05 GEMM with fused statistics + normalise/activate
+        assert _lib.launch_count - c0 <= 3            # [weight transpose +] tcgen05 GEMM with fused statistics + normalise/activate
         orig = tf_util._fused_dense_bn
         tf_util._fused_dense_bn = lambda *a, **k: None
         try:
