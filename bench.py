@@ -122,11 +122,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ per-kernel model
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-TRAFFIC_NCU = {
-    ("pasnl_gemm_rows_tf32x3", (262144, 128, 128)): 134382080 + 83796736,   # profiles/r01b_ncu_full_gemm_rows_persist_*.csv
-    ("pasnl_gemm_wgrad_tf32x3", (262144, 128, 128)): 268592896,            # profiles/r01b_ncu_full_gemm_wgrad_tm_*.csv
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture of the current
+# build: profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the raw ncu CSV (keys "entry_point|d0,d1,d2").
+def load_ncu_traffic():
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    return json.load(open(path)).get("traffic", {})
 
 
 def gemm_bound(nbytes, flops):
@@ -199,13 +201,72 @@ def algorithmic_work(name, a):
     if name == "pasnl_gemm_wgrad_tf32x3":
         rows, m, n = a[0:3]
         return 4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n, gemm_bound(4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n)
-    if name == "pasnl_bn_act_fwd":       # stats read + apply read/write of the (rows, c) activation
-        rows, c = a[0:2]
-        return 12 * rows * c, 8 * rows * c, "hbm"
+    if name == "pasnl_bn_act_fwd":       # apply reads y and writes out; + one more read of y when the statistics
+        rows, c = a[0:2]                 # were not already produced by the GEMM epilogue (stats_ready = argument 15)
+        stats_ready = bool(a[15]) if len(a) > 15 and isinstance(a[15], int) else False
+        return (8 if stats_ready else 12) * rows * c, 8 * rows * c, "hbm"
     if name == "pasnl_bn_act_bwd":       # reduce reads y, dout; apply reads y, dout, writes dy
         rows, c = a[0:2]
         return 20 * rows * c, 16 * rows * c, "hbm"
+    if name == "pasnl_gemm_rows_ws":
+        rows, k, n = a[0:3]
+        return 4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n, gemm_bound(4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n)
+    if name == "pasnl_pointconv_fwd":    # x (G,K,C) + w (G,K,32) in, (G,C,32) out
+        g, k, c = a[0:3]
+        return 4 * g * (k * c + 32 * k + 32 * c), 2 * g * k * c * 32, "hbm"
+    if name == "pasnl_pointconv_bwd":    # x, w, grad_out in; grad_x, grad_w out
+        g, k, c = a[0:3]
+        return 4 * g * (2 * k * c + 2 * 32 * k + 32 * c), 4 * g * k * c * 32, "hbm"
+    if name in ("pasnl_maxpool_k", "pasnl_maxpool_k_mask"):
+        g, k, c = a[0:3]
+        return 4 * g * k * c + (4 if name == "pasnl_maxpool_k" else 12) * g * c, g * k * c, "hbm"
+    if name == "pasnl_maxpool_k_grad":   # x, out, grad_out in; dense grad_x out
+        g, k, c = a[0:3]
+        return 8 * g * k * c + 8 * g * c, g * k * c, "hbm"
+    if name == "pasnl_maxpool_k_scatter":   # mask + grad_out in; ~one 32-byte sector read-modify-written per (g, c)
+        g, k, c = a[0:3]
+        return 12 * g * c + 64 * g * c, g * c, "hbm"
+    if name == "pasnl_add_cols":
+        rows, nc = a[0:2]
+        return 12 * rows * nc, rows * nc, "hbm"
+    if name == "pasnl_add_n":
+        n = a[0]
+        return 4 * n * (4 if a[3] else 3), n * (2 if a[3] else 1), "hbm"
+    if name in ("pasnl_concat_cols", "pasnl_split_cols"):
+        rows, ca, cb = a[0:3]
+        return 8 * rows * (ca + cb), 0, "hbm"
+    if name in ("pasnl_bias_add", "pasnl_col_sum"):
+        rows, n = a[0:2]
+        return (8 if name == "pasnl_bias_add" else 4) * rows * n, rows * n, "hbm"
+    if name == "pasnl_dropout":
+        return 8 * a[0], 4 * a[0], "hbm"
+    if name in ("pasnl_gemm_skinny",):
+        rows, ni, nj = a[0:3]
+        return 4 * (rows * ni + ni * nj + rows * nj), 2 * rows * ni * nj, "hbm"
+    if name == "pasnl_wgrad_skinny":
+        rows, ni, nj = a[0:3]
+        return 4 * (rows * ni + rows * nj + ni * nj), 2 * rows * ni * nj, "hbm"
+    if name in ("pasnl_softmax_ce_fwd", "pasnl_softmax_ce_bwd"):
+        rows, c = a[0:2]
+        return (4 if name.endswith("fwd") else 8) * rows * c + 16 * rows, 8 * rows * c, "hbm"
+    if name == "pasnl_adam_l2":          # p, g, m, v read; p, m, v written; 1-byte mask
+        return 29 * a[0], 12 * a[0], "hbm"
     return 0, 0, "hbm"
+
+
+FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop at the 1965 MHz the box runs
+
+
+def roof_seconds(nbytes, flops, bound, peaks):
+    """Time one launch would take AT its roof: max(bytes / HBM peak, flops / pipe peak).  3xTF32 runs three tensor
+    passes at half the bf16 rate (peak/6); distance kernels are held to the fp32 SIMT peak; latency-bound ops (FPS) are
+    only charged their compulsory bytes."""
+    t = nbytes / (peaks["hbm_gbs"] * 1e9)
+    if bound == "tensor":
+        t = max(t, 6.0 * flops / (peaks["bf16_tflops"] * 1e12))
+    elif bound == "fp32":
+        t = max(t, flops / (FP32_SIMT_TFLOPS * 1e12))
+    return t
 
 
 class KernelProfiler:
@@ -246,6 +307,7 @@ class KernelProfiler:
         for r in agg.values():
             avg = r["ms"] / r["calls"]
             rows.append({**r, "avg_us": 1e3 * avg, "ms_per_step": r["ms"] / steps,
+                         "roof_ms_per_step": 1e3 * roof_seconds(r["bytes"], r["flops"], r["bound"], load_peaks()) * r["calls"] / steps,
                          "gbs": r["bytes"] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0,
                          "tflops": r["flops"] / (avg * 1e-3) / 1e12 if avg > 0 else 0.0})
         rows.sort(key=lambda r: -r["ms_per_step"])
@@ -253,16 +315,19 @@ class KernelProfiler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0):
+def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0, full_batch=False):
     """The reference's algorithm on host cores: oracle/model_ref.py (line-by-line restatement of the TF graph code,
     reference-native nanoflann kNN / three_nn / three_interpolate where oracle/_ref has them, C restatement for the
     GPU-only ops).  Bounded sample: `sample_batch` clouds per step (per-cloud work is independent apart from the
     batch-norm statistics, so clouds/s scales linearly), thread count chosen by a short scan because the 1x1-conv
     stack on 10^5-row tensors scales badly past a few dozen threads.
-    Returns (clouds_per_s, ms_per_step, threads_used, kind, sample description)."""
+    Returns (clouds_per_s, ms_per_step, threads_used, kind, sample description, host core count)."""
     from oracle import cref, model_ref, refnative
     cores = os.cpu_count() or 1
+    # the in-line cpu_baseline leg times a bounded sample; `--impl reference` (full_batch) runs the whole cls batch
     sample_batch = min(batch, 8 if args.workload == "cls" else (2 if args.workload == "seg" else 1))
+    if full_batch and args.workload == "cls":
+        sample_batch = batch
     pc, labels, smpw = make_batch(args.workload, sample_batch, points, 1)
     x = torch.from_numpy(pc)
     y = torch.from_numpy(labels)
@@ -318,7 +383,7 @@ def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0):
     sample = (f"{done} step(s) of {sample_batch} clouds (of the {batch}-cloud batch) after a thread scan "
               f"(best of 8/16/32/64/{cores}: {threads} threads); torch CPU + reference-native nanoflann kNN / three_nn / "
               "three_interpolate (oracle/_ref), FPS and gathers from the C restatement (the reference has no CPU FPS)")
-    return sample_batch * done / dt, 1e3 * dt / done, threads, kind, sample
+    return sample_batch * done / dt, 1e3 * dt / done, threads, kind, sample, cores
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -354,11 +419,12 @@ def main():
         # bounded sample: a few full steps of the same workload on all host cores
         steps = max(1, min(args.steps, 3))
         warm = 0
-        val, ms, cores, kind, sample = run_cpu_reference(args, batch, points, steps, warm)
+        val, ms, threads, kind, sample, cores = run_cpu_reference(args, batch, points, steps, warm, full_batch=True)
         line = {"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                 "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "threads": threads, "kind": kind,
+                                 "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
@@ -471,7 +537,8 @@ def main():
     else:
         roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": top["gbs"] / peaks["hbm_gbs"]}
-    roof.update({"traffic": TRAFFIC_NCU.get((top["name"], tuple(top["dims"]))), "kernel": top["name"], "dims": top["dims"],
+    traffic = load_ncu_traffic().get(top["name"] + "|" + ",".join(str(d) for d in top["dims"][:3]))
+    roof.update({"traffic": traffic, "kernel": top["name"], "dims": top["dims"],
                  "avg_us": top["avg_us"], "entry_point_ms_per_step": by_name[top_name],
                  "native_bound": top["bound"], "peak_source": peaks["src"],
                  "timing": f"CUDA events around each launch, eager pass of {prof_steps} steps",
@@ -479,6 +546,20 @@ def main():
                  # CPU-launch bound, so the ratio understates the share; under ncu the library is 88 % of the device
                  # time of a step: profiles/r01c_launches_cls_step.csv)
                  "pasnl_ms_per_step_eager_events": ours_ms, "eager_ms_per_step": eager_ms})
+    # whole-step hot-path roofline: every library launch at ITS roof, against the graph-replayed step
+    ideal_ms = sum(r["roof_ms_per_step"] for r in rows)
+    by_roof = {}
+    for r in rows:
+        e = by_roof.setdefault(r["name"], [0.0, 0.0])
+        e[0] += r["ms_per_step"]
+        e[1] += r["roof_ms_per_step"]
+    step_roof = {"ideal_ms_per_step": ideal_ms, "clouds_per_s_at_roof": batch / (ideal_ms * 1e-3) if ideal_ms > 0 else None,
+                 "measured_ms_per_step": total_ms / args.steps, "frac": ideal_ms / (total_ms / args.steps),
+                 "definition": "sum over library launches of max(algorithmic bytes / HBM peak, flops / pipe peak); "
+                               "3xTF32 tensor peak = bf16 peak / 6, fp32 SIMT peak = %.1f TFLOP/s" % FP32_SIMT_TFLOPS,
+                 "per_op": [{"op": k, "ms": round(v[0], 4), "roof_ms": round(v[1], 4),
+                             "frac": round(v[1] / v[0], 3) if v[0] > 0 else None}
+                            for k, v in sorted(by_roof.items(), key=lambda kv: -kv[1][0])[:14]]}
     if args.kernel_report:
         os.makedirs(os.path.dirname(os.path.abspath(args.kernel_report)), exist_ok=True)
         json.dump({"eager_ms_per_step": eager_ms, "pasnl_ms_per_step": ours_ms, "peaks": peaks, "kernels": rows},
@@ -488,8 +569,8 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, ms, cores, kind, sample = run_cpu_reference(args, batch, points, steps=2, warmup=0, budget_s=30.0)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            v, ms, threads, kind, sample, cores = run_cpu_reference(args, batch, points, steps=2, warmup=0, budget_s=30.0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "threads": threads, "kind": kind, "sample": sample}
         except Exception as e:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
@@ -501,7 +582,7 @@ def main():
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

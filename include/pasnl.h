@@ -266,6 +266,7 @@ int pasnl_maxpool_k_mask(long groups, int k, int c, const float *x, float *out, 
 int pasnl_maxpool_k_scatter(long groups, int k, int c, const unsigned long long *mask, const float *grad_out,
                             float *grad_x, void *stream);
 int pasnl_add_cols(long rows, int nc, const float *src, float *dst, long ldd, void *stream);
+int pasnl_take_cols(long rows, int nc, const float *src, long lds, float *dst, void *stream);   /* dst = src[:, :nc] */
 /* dst_i (cols_i, rows_i) = src_i (rows_i, cols_i)^T for `count` matrices in one launch; table (device) holds
  * {src, dst, rows, cols} as 4 int64 per matrix; max_tiles = the largest ceil(rows/32)*ceil(cols/32). */
 int pasnl_transpose_batched(int count, const long *table, int max_tiles, void *stream);
@@ -274,6 +275,20 @@ int pasnl_transpose_batched(int count, const long *table, int max_tiles, void *s
  * bias).  pasnl_col_sum: out[c] = sum_r x[r][c] (the bias gradient). */
 int pasnl_bias_add(long rows, int n, const float *x, const float *bias, float *out, void *stream);
 int pasnl_col_sum(long rows, int n, const float *x, float *out, void *stream);
+
+/* ---------------------------------------------------------------- grid subsampling
+ * Replaces grid_subsampling(original_points, subsampled_points, original_features, subsampled_features,
+ * original_classes, subsampled_classes, sampleDl, verbose) of utils/cpp_wrappers/cpp_subsampling/grid_subsampling/
+ * grid_subsampling.cpp:5-106 (what cpp_subsampling.compute(points, features=, classes=, sampleDl=) runs,
+ * ScanNet/scannet_dataset_grid.py:20-38).  points (n,3) f32, features (n,fdim) f32 or NULL, classes (n,ldim) i32 or NULL
+ * -> *num_out occupied cells (device int), sub_points (<= n,3), sub_features (<= n,fdim), sub_classes (<= n,ldim): the
+ * caller allocates capacity n and reads *num_out.  Barycentres / feature means are bit-exact (fp32 sums in ascending
+ * point index, as the reference's sequential loop); cells are emitted in order of first appearance in the input and
+ * label ties go to the smallest label (the reference leaves both to its unordered_map's iteration order). */
+size_t pasnl_grid_subsample_workspace_bytes(int n);
+int pasnl_grid_subsample(int n, const float *points, int fdim, const float *features, int ldim, const int *classes,
+                         float sample_dl, void *workspace, int *num_out, float *sub_points, float *sub_features,
+                         int *sub_classes, void *stream);
 
 #ifdef __cplusplus
 }

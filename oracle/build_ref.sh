@@ -32,4 +32,10 @@ g++ -O2 -std=c++11 -fopenmp -fPIC -shared -I"$REF/utils/nearest_neighbors" \
   sed -n '60,153p' "$REF/tf_ops/3d_interpolation/tf_interpolate.cpp"
   echo '}'
 } | g++ -O2 -fPIC -shared -x c++ - -o "$OUT/ref_interp.so"
+# (4) CPU oracle for grid subsampling: the reference's grid_subsampling.cpp + cloud.cpp as they are, plus a 30-line
+#     extern "C" shim of ours (oracle/ref_shims/) in place of the CPython wrapper (wrapper.cpp needs numpy headers).
+CW="$REF/utils/cpp_wrappers"
+g++ -O2 -std=c++11 -fPIC -shared -I"$CW/cpp_subsampling" -o "$OUT/ref_gridsub.so" \
+    "$HERE/ref_shims/grid_subsampling_shim.cpp" "$CW/cpp_subsampling/grid_subsampling/grid_subsampling.cpp" \
+    "$CW/cpp_utils/cloud/cloud.cpp"
 echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')"

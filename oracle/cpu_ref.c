@@ -368,3 +368,93 @@ void oracle_three_interpolate_grad(int b, int n, int c, int m, const float *grad
             }
         }
 }
+
+
+/* ---------------------------------------------------------------------------------------------- grid subsampling
+ * utils/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106 with SampledData of
+ * grid_subsampling.h:12-88: one pass over the points in index order, per cell count / fp32 point sum / fp32 feature
+ * sums / label histograms, then barycentre = sum * (float)(1.0 / count), feature = sum / (float)count, label = most
+ * frequent.  fp32 arithmetic statement by statement (:24-31 origin and grid size, :52-55 cell index).
+ * Pinned where the reference is implementation-defined (std::unordered_map iteration order): cells are emitted in
+ * order of first appearance, label ties go to the smallest label.  Returns the number of cells. */
+static int cmp_key_idx(const void *a, const void *b) {
+    const unsigned long long *x = (const unsigned long long *)a, *y = (const unsigned long long *)b;
+    if (x[0] != y[0]) return x[0] < y[0] ? -1 : 1;
+    return x[1] < y[1] ? -1 : (x[1] > y[1] ? 1 : 0);
+}
+static int cmp_first(const void *a, const void *b) {
+    const long *x = (const long *)a, *y = (const long *)b;
+    return x[0] < y[0] ? -1 : (x[0] > y[0] ? 1 : 0);
+}
+int oracle_grid_subsample_ex(int n, const float *pts, int fdim, const float *feats, int ldim, const int *classes, float dl,
+                             float *out_pts, float *out_feats, int *out_classes, int tie_largest);
+int oracle_grid_subsample(int n, const float *pts, int fdim, const float *feats, int ldim, const int *classes, float dl,
+                          float *out_pts, float *out_feats, int *out_classes) {
+    return oracle_grid_subsample_ex(n, pts, fdim, feats, ldim, classes, dl, out_pts, out_feats, out_classes, 0);
+}
+/* tie_largest != 0: label ties go to the LARGEST label instead -- used by the tests to tell a tie (where the
+ * reference's answer is implementation-defined) from a real disagreement */
+int oracle_grid_subsample_ex(int n, const float *pts, int fdim, const float *feats, int ldim, const int *classes, float dl,
+                             float *out_pts, float *out_feats, int *out_classes, int tie_largest) {
+    if (n <= 0) return 0;
+    float mn[3] = {pts[0], pts[1], pts[2]}, mx[3] = {pts[0], pts[1], pts[2]};
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) {
+            if (pts[3 * i + d] < mn[d]) mn[d] = pts[3 * i + d];
+            if (pts[3 * i + d] > mx[d]) mx[d] = pts[3 * i + d];
+        }
+    const float inv = 1 / dl;
+    float org[3];
+    for (int d = 0; d < 3; ++d) org[d] = floorf(mn[d] * inv) * dl;
+    const unsigned long long nx = (unsigned long long)floorf((mx[0] - org[0]) / dl) + 1;
+    const unsigned long long ny = (unsigned long long)floorf((mx[1] - org[1]) / dl) + 1;
+    unsigned long long *ki = (unsigned long long *)malloc(sizeof(unsigned long long) * 2 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long ix = (unsigned long long)floorf((pts[3 * i] - org[0]) / dl);
+        const unsigned long long iy = (unsigned long long)floorf((pts[3 * i + 1] - org[1]) / dl);
+        const unsigned long long iz = (unsigned long long)floorf((pts[3 * i + 2] - org[2]) / dl);
+        ki[2 * i] = ix + nx * iy + nx * ny * iz;
+        ki[2 * i + 1] = (unsigned long long)i;
+    }
+    qsort(ki, (size_t)n, 2 * sizeof(unsigned long long), cmp_key_idx);      /* cells contiguous, points ascending inside */
+    long *cells = (long *)malloc(sizeof(long) * 3 * (size_t)n);             /* (first index, start, count) */
+    int nc = 0;
+    for (int a = 0; a < n;) {
+        int b = a;
+        while (b < n && ki[2 * b] == ki[2 * a]) ++b;
+        cells[3 * nc] = (long)ki[2 * a + 1];
+        cells[3 * nc + 1] = a;
+        cells[3 * nc + 2] = b - a;
+        ++nc;
+        a = b;
+    }
+    qsort(cells, (size_t)nc, 3 * sizeof(long), cmp_first);                  /* order of first appearance */
+    for (int c = 0; c < nc; ++c) {
+        const long a0 = cells[3 * c + 1], cnt = cells[3 * c + 2];
+        float s[3] = {0.f, 0.f, 0.f};
+        for (long a = a0; a < a0 + cnt; ++a) {
+            const long i = (long)ki[2 * a + 1];
+            s[0] += pts[3 * i]; s[1] += pts[3 * i + 1]; s[2] += pts[3 * i + 2];
+        }
+        const float w = (float)(1.0 / (double)cnt);
+        out_pts[3 * c] = s[0] * w; out_pts[3 * c + 1] = s[1] * w; out_pts[3 * c + 2] = s[2] * w;
+        for (int f = 0; f < fdim; ++f) {
+            float t = 0.f;
+            for (long a = a0; a < a0 + cnt; ++a) t += feats[(long)ki[2 * a + 1] * fdim + f];
+            out_feats[(long)c * fdim + f] = t / (float)cnt;
+        }
+        for (int l = 0; l < ldim; ++l) {
+            int best = 0, bestc = 0;
+            for (long a = a0; a < a0 + cnt; ++a) {
+                const int v = classes[(long)ki[2 * a + 1] * ldim + l];
+                int k = 0;
+                for (long b = a0; b < a0 + cnt; ++b) k += classes[(long)ki[2 * b + 1] * ldim + l] == v;
+                if (k > bestc || (k == bestc && (tie_largest ? v > best : v < best))) { best = v; bestc = k; }
+            }
+            out_classes[(long)c * ldim + l] = best;
+        }
+    }
+    free(ki);
+    free(cells);
+    return nc;
+}

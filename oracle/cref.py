@@ -151,3 +151,27 @@ def three_interpolate_grad(m, idx, weight, grad_out):
     g = np.empty((b, m, c), np.float32)
     lib().oracle_three_interpolate_grad(b, n, c, m, _fp(grad_out), _ip(idx), _fp(weight), _fp(g))
     return g
+
+
+def grid_subsample(points, features=None, classes=None, dl=0.1, tie_largest=False):
+    """oracle_grid_subsample (grid_subsampling.cpp:5-106): -> sub_points [, sub_features] [, sub_classes]; cells in order
+    of first appearance, label ties -> smallest label."""
+    pts = _f32(points)
+    n = pts.shape[0]
+    feats = _f32(features) if features is not None else None
+    cls = _i32(classes).reshape(n, -1) if classes is not None else None
+    fdim = 0 if feats is None else feats.shape[1]
+    ldim = 0 if cls is None else cls.shape[1]
+    op = np.empty((n, 3), np.float32)
+    of = np.empty((n, max(fdim, 1)), np.float32)
+    oc = np.empty((n, max(ldim, 1)), np.int32)
+    fn = lib().oracle_grid_subsample_ex
+    fn.restype = ctypes.c_int
+    m = fn(n, _fp(pts), fdim, _fp(feats) if feats is not None else None, ldim, _ip(cls) if cls is not None else None,
+           ctypes.c_float(dl), _fp(op), _fp(of), _ip(oc), 1 if tie_largest else 0)
+    out = [op[:m]]
+    if fdim:
+        out.append(of[:m, :fdim])
+    if ldim:
+        out.append(oc[:m, :ldim])
+    return out[0] if len(out) == 1 else tuple(out)

@@ -92,6 +92,31 @@ def three_interpolate_grad(m, idx, weight, grad_out):
     return g
 
 
+def grid_subsampling(points, features=None, classes=None, dl=0.1):
+    """The reference's grid_subsampling() (grid_subsampling.cpp:5-106) through oracle/ref_shims; outputs in the
+    reference's own unordered_map iteration order."""
+    pts = np.ascontiguousarray(points, np.float32)
+    n = pts.shape[0]
+    feats = np.ascontiguousarray(features, np.float32) if features is not None else None
+    cls = np.ascontiguousarray(classes, np.int32).reshape(n, -1) if classes is not None else None
+    fdim = 0 if feats is None else feats.shape[1]
+    ldim = 0 if cls is None else cls.shape[1]
+    op = np.empty((n, 3), np.float32)
+    of = np.empty((n, max(fdim, 1)), np.float32)
+    oc = np.empty((n, max(ldim, 1)), np.int32)
+    fn = _lib("ref_gridsub.so").ref_grid_subsampling
+    fn.restype = ctypes.c_int
+    m = fn(n, pts.ctypes.data_as(_f), fdim, feats.ctypes.data_as(_f) if feats is not None else None, ldim,
+           cls.ctypes.data_as(_i) if cls is not None else None, ctypes.c_float(dl), op.ctypes.data_as(_f),
+           of.ctypes.data_as(_f), oc.ctypes.data_as(_i))
+    out = [op[:m]]
+    if fdim:
+        out.append(of[:m].reshape(m, fdim))
+    if ldim:
+        out.append(oc[:m].reshape(m, ldim))
+    return out[0] if len(out) == 1 else tuple(out)
+
+
 # ---------------------------------------------------------------- GPU pieces (torch CUDA tensors)
 def _p(t):
     return ctypes.c_void_p(t.data_ptr())

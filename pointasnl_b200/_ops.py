@@ -618,23 +618,13 @@ def gemm_rows(a, w, w_kn=False, col_stats=None):
               _ptr(c), n, _ptr(col_stats), None, None, 0, _stream())
         return c if col_stats is None else (c, True)
     bt = transposed_weight(w) if w_kn else w
-    # The TMEM accumulator truncates on every add (error ~3e-8 * k * |C|): long contractions are cut into <= 1024-wide
-    # slabs whose partial products are summed with round-to-nearest fp32 adds.  (Long k only occurs with few rows --
-    # the PointConv `after_conv`, 2048/4096 wide on 16384/4096 rows -- so the extra pass is tiny, and the slabs give
-    # the small row grid more CTAs.)
+    # (contractions longer than 1024 run inside the library as side-by-side <= 1024-wide slabs added into a zeroed C:
+    #  the TMEM accumulator truncates on every add, ~3e-8 * k relative; statistics are then left to the BN kernel)
     fuse_stats = col_stats is not None and k <= GEMM_K_SLAB
-    out = None
-    for k0 in range(0, k, GEMM_K_SLAB):
-        kk = min(GEMM_K_SLAB, k - k0)
-        c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
-        asl, bsl = a[:, k0:k0 + kk], bt[:, k0:k0 + kk]
-        _call("pasnl_gemm_rows_tf32x3", rows, kk, n, asl.data_ptr(), int(a.stride(0)), bsl.data_ptr(), int(bt.stride(0)),
-              _ptr(c), n, _ptr(col_stats) if fuse_stats else None, _stream())
-        if out is None:
-            out = c
-        else:
-            _call("pasnl_add_n", out.numel(), _ptr(out), _ptr(c), None, _ptr(out), _stream())
-    return out if col_stats is None else (out, fuse_stats)
+    c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
+    _call("pasnl_gemm_rows_tf32x3", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(bt), int(bt.stride(0)), _ptr(c), n,
+          _ptr(col_stats) if fuse_stats else None, _stream())
+    return c if col_stats is None else (c, fuse_stats)
 
 
 def _bn_single_launch(rows, c):
@@ -904,7 +894,7 @@ class SAFront(torch.autograd.Function):
         mask = torch.empty((b, s, w), device=x.device, dtype=torch.int64)
         _call("pasnl_maxpool_k_mask", b * s, k, w, _ptr(x), _ptr(pooled), _ptr(mask), _stream())
         xyz = torch.empty((b, s, k, 3), device=x.device, dtype=torch.float32)
-        _call("pasnl_split_cols", b * s * k, 3, w - 3, _ptr(x), _ptr(xyz), None, _stream())
+        _call("pasnl_take_cols", b * s * k, 3, _ptr(x), w, _ptr(xyz), _stream())
         ctx.save_for_backward(mask)
         ctx.dims = (b, s, k, w)
         ident = x.view_as(x)

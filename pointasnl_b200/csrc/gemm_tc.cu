@@ -201,8 +201,18 @@ template <int NT, bool VEC4>
 __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, int n, const float *__restrict__ A,
                                                              long lda, const float *__restrict__ Bt, long ldb,
                                                              float *__restrict__ C, long ldc,
-                                                             double *__restrict__ stats) {
+                                                             double *__restrict__ stats, int kslab) {
     constexpr int kStage = 2 * kM * kKC + 2 * NT * kKC;            // floats per operand stage (A hi/lo, B hi/lo)
+    // split-k (gridDim.z > 1): this CTA contracts columns [z*kslab, (z+1)*kslab) and ADDS its tile into a zeroed C.
+    // Long contractions are cut anyway (the TMEM adder truncates, ~3e-8*k relative: <= 1024-wide slabs summed with
+    // round-to-nearest adds); running the slabs side by side fills the GPU when there are few row tiles.
+    const bool split = gridDim.z > 1;
+    {
+        const int kz = blockIdx.z * kslab;
+        A += kz;
+        Bt += kz;
+        k = min(kslab, k - kz);
+    }
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t bar[2];                                    // "stage s has been consumed by the tensor core"
     __shared__ uint32_t tmem_slot;
@@ -329,7 +339,12 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
             if (grow < rows && gcol < n) {
                 const float4 v = *reinterpret_cast<const float4 *>(stage + r * PP + c);
                 float *dst = C + grow * ldc + gcol;
-                if (gcol + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                if (split) {
+                    atomicAdd(dst, v.x);
+                    if (gcol + 1 < n) atomicAdd(dst + 1, v.y);
+                    if (gcol + 2 < n) atomicAdd(dst + 2, v.z);
+                    if (gcol + 3 < n) atomicAdd(dst + 3, v.w);
+                } else if (gcol + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
                     *reinterpret_cast<float4 *>(dst) = v;
                 } else {
                     dst[0] = v.x;
@@ -349,22 +364,22 @@ __global__ void __launch_bounds__(kThreads) gemm_rows_kernel(long rows, int k, i
 
 template <int NT>
 int launch(long rows, int k, int n, const float *A, long lda, const float *Bt, long ldb, float *C, long ldc,
-           double *stats, cudaStream_t st) {
+           double *stats, int kslab, cudaStream_t st) {
     const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(Bt) & 15u) == 0);
     const size_t smem = sizeof(float) * 2 * (size_t)(2 * kM * kKC + 2 * NT * kKC);   // two operand stages
-    dim3 grid((unsigned)((rows + kM - 1) / kM), (unsigned)((n + NT - 1) / NT));
+    dim3 grid((unsigned)((rows + kM - 1) / kM), (unsigned)((n + NT - 1) / NT), (unsigned)((k + kslab - 1) / kslab));
     cudaError_t e;
     if (vec) {
         auto kern = gemm_rows_kernel<NT, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc, stats);
+        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc, stats, kslab);
     } else {
         auto kern = gemm_rows_kernel<NT, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc, stats);
+        kern<<<grid, kThreads, smem, st>>>(rows, k, n, A, lda, Bt, ldb, C, ldc, stats, kslab);
     }
     return pasnl_launch_status();
 }
@@ -687,6 +702,16 @@ inline int sm_count() {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
     return sms;
+}
+
+inline int min_tile_width() {               // PASNL_ROWS_MIN_NT: floor of the narrowing heuristic (default 32)
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("PASNL_ROWS_MIN_NT");
+        v = e ? atoi(e) : 32;
+        if (v != 32 && v != 64 && v != 128 && v != 256) v = 32;
+    }
+    return v;
 }
 
 constexpr long kSmemBudget = 227 * 1024 - 2048;   // opt-in maximum minus the static barriers / slack
@@ -1355,11 +1380,28 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
         if (gtc::persist_stages(kpad, nt) >= 2)
             return gtc::launch_persist_cols(rows, k, n, 0, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
     }
-    // UMMA N must be a multiple of 16 (M = 128): the tile is padded in shared memory, stores are bounds-checked
-    if (n <= 32) return gtc::launch<32>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
-    if (n <= 64) return gtc::launch<64>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
-    if (n <= 128) return gtc::launch<128>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
-    return gtc::launch<256>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, st);
+    // UMMA N must be a multiple of 16 (M = 128): the tile is padded in shared memory, stores are bounds-checked.
+    // Tile width: as wide as n allows (each CTA splits its A rows once per output tile), but a layer with few row tiles
+    // (rows = 4096: the classifier heads, the deep seg layers) takes narrower tiles until the grid covers the SMs.
+    // contractions longer than 1024 run as side-by-side <= 1024-wide slabs that add into a zeroed C (split-k)
+    const int kslab = k > 1024 ? 1024 : k;
+    const int nz = (k + kslab - 1) / kslab;
+    if (nz > 1) {
+        PASNL_CHECK_ARG(col_stats == nullptr);
+        cudaError_t me = cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)n, (size_t)rows, st);
+        if (me != cudaSuccess) return (int)me;
+    }
+    int nt = n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256));
+    const long row_tiles = (rows + gtc::kM - 1) / gtc::kM;
+    while (nt > gtc::min_tile_width() && row_tiles * ((n + nt - 1) / nt) * nz < gtc::sm_count() * 3 / 4) nt >>= 1;
+    if (const char *e = getenv("PASNL_ROWS_NT")) {            // measurement override (tools/sweep_small_gemm.py)
+        const int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128 || v == 256) nt = v;
+    }
+    if (nt == 32) return gtc::launch<32>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, kslab, st);
+    if (nt == 64) return gtc::launch<64>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, kslab, st);
+    if (nt == 128) return gtc::launch<128>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, kslab, st);
+    return gtc::launch<256>(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, kslab, st);
 }
 
 extern "C" int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy,

@@ -239,8 +239,13 @@ __global__ void adam_l2_kernel(long n, float *__restrict__ p, const float *__res
                                float grad_scale, float lr, float b1, float b2, float eps, const long *__restrict__ step,
                                double *__restrict__ reg) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const double t = (double)(__ldg(step) + 1);
-    const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
+    __shared__ float s_lr_t;
+    if (threadIdx.x == 0) {               // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), once per block
+        const double t = (double)(__ldg(step) + 1);
+        s_lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+    }
+    __syncthreads();
+    const float lr_t = s_lr_t;
     float r = 0.f;
     if (i < n) {
         const float pi = p[i];
@@ -254,7 +259,7 @@ __global__ void adam_l2_kernel(long n, float *__restrict__ p, const float *__res
         m[i] = mi;
         v[i] = vi;
         // tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)
-        p[i] = pi - lr * sqrtf(bc2) / bc1 * mi / (sqrtf(vi) + eps);
+        p[i] = pi - lr_t * mi / (sqrtf(vi) + eps);
     }
     if (reg) {
 #pragma unroll
@@ -316,6 +321,14 @@ __global__ void __launch_bounds__(256) maxpool_k_scatter_kernel(long gc, int k, 
             q[(long)t * c] += share;
         }
     }
+}
+// dst[r][0..nc) = src[r][0..nc) (src row pitch lds): the leading-column slice as a dense tensor
+__global__ void take_cols_kernel(long rows, int nc, const float *__restrict__ src, long lds, float *__restrict__ dst) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * nc) return;
+    const long r = e / nc;
+    const int c = (int)(e - r * nc);
+    dst[e] = __ldg(src + r * lds + c);
 }
 // dst[r][0..nc) += src[r][0..nc)  (dst row pitch ldd): the gradient of a leading-column slice, added in place
 __global__ void add_cols_kernel(long rows, int nc, const float *__restrict__ src, float *__restrict__ dst, long ldd) {
@@ -540,5 +553,13 @@ extern "C" int pasnl_col_sum(long rows, int n, const float *x, float *out, void 
     if (slabs > 256) slabs = 256;
     const dim3 grid((unsigned)((n + 31) / 32), (unsigned)slabs);
     sops::col_sum_kernel<<<grid, 256, 0, st>>>(rows, n, x, out);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_take_cols(long rows, int nc, const float *src, long lds, float *dst, void *stream) {
+    PASNL_CHECK_ARG(rows >= 0 && nc >= 1 && lds >= nc && (rows == 0 || (src && dst)));
+    if (rows == 0) return PASNL_OK;
+    const long tot = rows * nc;
+    sops::take_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, nc, src, lds, dst);
     return pasnl_launch_status();
 }

@@ -40,6 +40,21 @@ def main():
     g = rng.normal(size=(2, 512, 7)).astype(np.float32)
     blob["ti_grad_out"] = g
     blob["ti_grad_points"] = refnative.three_interpolate_grad(128, i, w, g)
+    # grid subsampling: the reference's grid_subsampling.cpp (through oracle/ref_shims), rows sorted lexicographically
+    # because the reference's own output order is std::unordered_map iteration order
+    def sorted_rows(p, *rest):
+        order = np.lexsort((p[:, 2], p[:, 1], p[:, 0]))
+        return [p[order]] + [r[order] for r in rest]
+    rng = np.random.default_rng(9)
+    gp = (rng.uniform(-1.0, 1.0, (3000, 3)) * np.array([2.0, 1.5, 0.7])).astype(np.float32)
+    gp[100:200] = gp[0:100]                                  # exact duplicates
+    gf = rng.uniform(0, 1, (3000, 3)).astype(np.float32)
+    gl = np.repeat(rng.integers(0, 5, (750, 2)), 4, axis=0).astype(np.int32)     # runs of equal labels: few count ties
+    blob["gs_points"], blob["gs_features"], blob["gs_labels"] = gp, gf, gl
+    for dl, tag in ((0.1, "dl10"), (0.04, "dl04"), (0.5, "dl50")):
+        p_, f_, l_ = refnative.grid_subsampling(gp, gf, gl, dl)
+        p_, f_, l_ = sorted_rows(p_, f_, l_)
+        blob[f"gs_{tag}_points"], blob[f"gs_{tag}_features"], blob[f"gs_{tag}_labels"] = p_, f_, l_
     out = os.path.join(ROOT, "tests", "golden", "cpu_ref.npz")
     np.savez_compressed(out, **blob)
     print("wrote", out, os.path.getsize(out))

@@ -37,8 +37,9 @@ def test_rows_ws_matches_fp64(cuda, rows, k, n, w_kn):
     assert err < 5e-6
     # the statistics are those of the fp32 result the kernel wrote (what the batch-norm pass that follows normalises)
     cd = c.double()
-    torch.testing.assert_close(st[:n], cd.sum(0), rtol=1e-7, atol=2e-7 * scale * rows ** 0.5)
-    torch.testing.assert_close(st[n:], (cd * cd).sum(0), rtol=2e-7, atol=1e-9)
+    # (fp32 partial sums per 128-row tile, fp64 across tiles: ~1e-7 of sum |x|)
+    torch.testing.assert_close(st[:n], cd.sum(0), rtol=1e-7, atol=2e-7 * scale * rows)
+    torch.testing.assert_close(st[n:], (cd * cd).sum(0), rtol=1e-6, atol=1e-9)
 
 
 @pytest.mark.parametrize("act", [0, 1, 2])
