@@ -205,9 +205,10 @@ def test_grid_subsampling_oracle_order_and_properties():
     same = (cell0 == cell0[0]).all(1)
     np.testing.assert_allclose(p[0], pts[same].mean(0), rtol=1e-5, atol=1e-6)
     assert len(p) == len(np.unique(cell0, axis=0))                         # one barycentre per occupied cell
-    # a cell size larger than the cloud gives one point: the centroid
-    one = cref.grid_subsample(pts, dl=10.0)
-    assert one.shape == (1, 3) and np.allclose(one[0], pts.mean(0), atol=1e-4)
+    # a cell that contains the whole cloud gives one point: the centroid (the grid origin is a multiple of dl)
+    pos = np.abs(pts) + np.float32(0.01)
+    one = cref.grid_subsample(pos, dl=10.0)
+    assert one.shape == (1, 3) and np.allclose(one[0], pos.mean(0), atol=1e-4)
 
 
 @pytest.mark.skipif(not refnative.available("ref_gridsub.so"), reason="oracle/_ref not built (no /root/reference)")
