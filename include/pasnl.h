@@ -290,6 +290,16 @@ int pasnl_grid_subsample(int n, const float *points, int fdim, const float *feat
                          float sample_dl, void *workspace, int *num_out, float *sub_points, float *sub_features,
                          int *sub_classes, void *stream);
 
+/* ---------------------------------------------------------------- ops exported by the reference's libraries but unused by its models
+ * pasnl_prob_sample replaces probsampleLauncher (tf_ops/sampling/tf_sampling_g.cu:194-197; ProbSample, tf_sampling.py:13-22):
+ * inp_p (b,n) non-negative weights, inp_r (b,m) uniform numbers in [0,1) -> out (b,m) = index of the first running sum
+ * >= r * total; temp (b,n) receives the running sums.  The fp32 summation order is the reference's, so indices match
+ * bit for bit.  pasnl_selection_sort replaces selectionSortLauncher (tf_grouping_g.cu:129-132; SelectionSort,
+ * tf_grouping.py:22-32): dist (b,m,n) -> outi, out (b,m,n) whose first k entries per row are the k smallest, ascending;
+ * same swap rule, so ties and the unsorted remainder land where the reference puts them. */
+int pasnl_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out, void *stream);
+int pasnl_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

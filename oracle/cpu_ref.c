@@ -458,3 +458,69 @@ int oracle_grid_subsample_ex(int n, const float *pts, int fdim, const float *fea
     free(cells);
     return nc;
 }
+
+
+/* ---------------------------------------------------------------------------------------------- prob_sample
+ * tf_sampling_g.cu:7-104 (cumsumKernel + binarysearchKernel).  The index returned depends on the rounding of the fp32
+ * running sums, so the summation tree is restated exactly: 8192-element blocks; inside a block groups of four
+ * (v1, v1+v2, v3+(v1+v2), (v4+v3)+(v2+v1)); the group totals go through an up-sweep / down-sweep scan (:44-63); element =
+ * (prefix in group + scanned total of the previous group) + carry; the carry between blocks is compensated (:73-76). */
+void oracle_cumsum(int b, int n, const float *inp, float *out) {
+    enum { BLK = 8192 };
+    float *pre = (float *)malloc(sizeof(float) * BLK), *tot = (float *)malloc(sizeof(float) * (BLK / 4));
+    for (int i = 0; i < b; ++i) {
+        const float *src = inp + (size_t)i * n;
+        float *dst = out + (size_t)i * n;
+        float carry = 0.f, comp = 0.f;
+        for (int j = 0; j < n; j += BLK) {
+            const int cnt = n - j < BLK ? n - j : BLK;
+            const int padded = (cnt + 3) & ~3, groups = padded >> 2;
+            for (int g = 0; g < groups; ++g) {
+                const int k = g * 4;
+                if (k + 3 < cnt) {
+                    const float v1 = src[j + k], v2 = src[j + k + 1], v3 = src[j + k + 2], v4 = src[j + k + 3];
+                    const float s12 = v2 + v1, s34 = v4 + v3;
+                    pre[k] = v1; pre[k + 1] = s12; pre[k + 2] = v3 + s12; pre[k + 3] = s34 + s12;
+                    tot[g] = pre[k + 3];
+                } else {
+                    float v = 0.f;
+                    for (int e = k; e < cnt; ++e) { v += src[j + e]; pre[e] = v; }
+                    for (int e = cnt; e < padded; ++e) pre[e] = v;
+                    tot[g] = v;
+                }
+            }
+            int u = 0;
+            for (; (2 << u) <= groups; ++u)
+                for (int q = 0; q < (groups >> (u + 1)); ++q)
+                    tot[(((q << 1) + 2) << u) - 1] += tot[(((q << 1) + 1) << u) - 1];
+            for (--u; u >= 0; --u)
+                for (int q = 0; q < ((groups - (1 << u)) >> (u + 1)); ++q)
+                    tot[(((q << 1) + 3) << u) - 1] += tot[(((q << 1) + 2) << u) - 1];
+            for (int e = 0; e < cnt; ++e) {
+                const int g = e >> 2;
+                const float in_block = g > 0 ? pre[e] + tot[g - 1] : pre[e];
+                dst[j + e] = in_block + carry;
+            }
+            const float t = tot[groups - 1] + comp;
+            const float r2 = carry + t;
+            comp = t - (r2 - carry);
+            carry = r2;
+        }
+    }
+    free(pre);
+    free(tot);
+}
+void oracle_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out) {
+    oracle_cumsum(b, n, inp_p, temp);
+    int base = 1;
+    while (base < n) base <<= 1;
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < m; ++j) {
+            const float *row = temp + (size_t)i * n;
+            const float q = inp_r[(size_t)i * m + j] * row[n - 1];
+            int r = n - 1;
+            for (int k = base; k >= 1; k >>= 1)
+                if (r >= k && row[r - k] >= q) r -= k;
+            out[(size_t)i * m + j] = r;
+        }
+}

@@ -175,3 +175,14 @@ def grid_subsample(points, features=None, classes=None, dl=0.1, tie_largest=Fals
     if ldim:
         out.append(oc[:m, :ldim])
     return out[0] if len(out) == 1 else tuple(out)
+
+
+def prob_sample(inp, inpr):
+    """oracle_prob_sample (tf_sampling_g.cu:7-104) -> (indices (b,m) int32, running sums (b,n) float32)."""
+    inp, inpr = _f32(inp), _f32(inpr)
+    b, n = inp.shape
+    m = inpr.shape[1]
+    temp = np.empty((b, n), np.float32)
+    out = np.empty((b, m), np.int32)
+    lib().oracle_prob_sample(b, n, m, _fp(inp), _fp(inpr), _fp(temp), _ip(out))
+    return out, temp

@@ -215,3 +215,18 @@ def gpu_selection_sort(k, dist):
     _lib("ref_grouping.so")._Z21selectionSortLauncheriiiiPKfPiPf(b, n, m, k, _p(dist), _p(outi), _p(out))
     _sync()
     return outi, out
+
+
+def gpu_prob_sample(inp, inpr):
+    """probsampleLauncher (tf_sampling_g.cu:194-197) -> (indices, running sums), torch CUDA tensors."""
+    import torch
+    b, n = inp.shape
+    m = inpr.shape[1]
+    inp = inp.contiguous().float()
+    inpr = inpr.contiguous().float()
+    temp = torch.empty((b, n), device=inp.device, dtype=torch.float32)
+    out = torch.zeros((b, m), device=inp.device, dtype=torch.int32)
+    _sync()
+    _lib("ref_sampling.so")._Z18probsampleLauncheriiiPKfS0_PfPi(b, n, m, _p(inp), _p(inpr), _p(temp), _p(out))
+    _sync()
+    return out, temp

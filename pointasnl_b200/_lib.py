@@ -67,6 +67,8 @@ SIGNATURES = {
     "pasnl_col_sum": (c_int, [c_long, c_int, P, P, P]),
     "pasnl_grid_subsample_workspace_bytes": (c_size_t, [c_int]),
     "pasnl_grid_subsample": (c_int, [c_int, P, c_int, P, c_int, P, c_float, P, P, P, P, P, P]),
+    "pasnl_prob_sample": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+    "pasnl_selection_sort": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "pasnl_bn_workspace_bytes": (c_size_t, [c_int]),
     "pasnl_bn_act_fwd": (c_int, [c_long, c_int, P, P, P, c_float, c_int, P, P, P, P, P, P, c_float, c_int, c_int, P, P]),
     "pasnl_bn_act_bwd": (c_int, [c_long, c_int, P, P, P, P, P, P, c_float, c_int, P, P, P, c_int, P, P]),
@@ -90,7 +92,7 @@ KERNELS_PER_CALL = {
     "pasnl_gather_point_grad": 2, "pasnl_gather_rows_grad": 2, "pasnl_group_point_grad": 2,
     "pasnl_three_interpolate_grad": 2, "pasnl_group_concat_grad": 4, "pasnl_nl_core_bwd": 3,
     "pasnl_bn_act_fwd": 3, "pasnl_bn_act_bwd": 3, "pasnl_gemm_wgrad_tf32x3": 2, "pasnl_softmax_ce_fwd": 2,
-    "pasnl_adam_l2": 2, "pasnl_col_sum": 2, "pasnl_grid_subsample": 15,
+    "pasnl_adam_l2": 2, "pasnl_col_sum": 2, "pasnl_grid_subsample": 15, "pasnl_prob_sample": 2,
 }
 
 

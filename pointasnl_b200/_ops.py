@@ -123,6 +123,29 @@ class GatherRows(torch.autograd.Function):
         return src_g, None
 
 
+def prob_sample(inp, inpr):
+    inp, inpr = _f32(inp, "inp"), _f32(inpr, "inpr")
+    _require(inp.dim() == 2, "ProbSample expects (batch_size,num_choices) inp shape")
+    _require(inpr.dim() == 2 and inpr.shape[0] == inp.shape[0], "ProbSample expects (batch_size,num_points) inpr shape")
+    b, n = inp.shape
+    m = inpr.shape[1]
+    temp = torch.empty((b, n), device=inp.device, dtype=torch.float32)
+    out = torch.empty((b, m), device=inp.device, dtype=torch.int32)
+    _call("pasnl_prob_sample", b, n, m, _ptr(inp), _ptr(inpr), _ptr(temp), _ptr(out), _stream())
+    return out
+
+
+def selection_sort(k, dist):
+    dist = _f32(dist, "dist")
+    _require(dist.dim() == 3, "SelectionSort expects (b,m,n) dist shape.")
+    _require(int(k) > 0, "SelectionSort expects positive k")
+    b, m, n = dist.shape
+    outi = torch.empty((b, m, n), device=dist.device, dtype=torch.int32)
+    out = torch.empty((b, m, n), device=dist.device, dtype=torch.float32)
+    _call("pasnl_selection_sort", b, n, m, int(k), _ptr(dist), _ptr(outi), _ptr(out), _stream())
+    return outi, out
+
+
 # ------------------------------------------------------------------ grouping
 def ball_query(radius, nsample, xyz1, xyz2):
     xyz1, xyz2 = _f32(xyz1, "xyz1"), _f32(xyz2, "xyz2")

@@ -5,7 +5,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _ops, tf_util
-from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss
+from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss, index_cache
 from ..pointnet_util import pointnet_sa_module
 
 # (scope, npoint, nsample, mlp) of the two set-abstraction layers, reference :33-36
@@ -24,6 +24,11 @@ def placeholder_inputs(batch_size, num_point, use_normal=False, device="cuda"):
 def get_model(point_cloud, is_training, use_normal=False, bn_decay=None, weight_decay=None, num_class=40,
               adaptive_sample=False):
     """point_cloud (B, N, 3 or 6) -> logits (B, num_class), end_points."""
+    with index_cache():
+        return _get_model(point_cloud, is_training, use_normal, bn_decay, weight_decay, num_class, adaptive_sample)
+
+
+def _get_model(point_cloud, is_training, use_normal, bn_decay, weight_decay, num_class, adaptive_sample):
     batch_size = point_cloud.shape[0]
     end_points = {}
     if use_normal and point_cloud.is_cuda:
@@ -36,10 +41,11 @@ def get_model(point_cloud, is_training, use_normal=False, bn_decay=None, weight_
     as_neighbor = [12, 12] if adaptive_sample else [0, 0]
 
     levels = []
-    for (scope, npoint, nsample, mlp), k_as in zip(SA_LAYERS, as_neighbor):
+    for li, ((scope, npoint, nsample, mlp), k_as) in enumerate(zip(SA_LAYERS, as_neighbor)):
+        nxt = (SA_LAYERS[li + 1][1], SA_LAYERS[li + 1][2]) if li + 1 < len(SA_LAYERS) else None
         xyz, points = PointASNLSetAbstraction(xyz, points, npoint=npoint, nsample=nsample, mlp=mlp,
                                               is_training=is_training, bn_decay=bn_decay, weight_decay=weight_decay,
-                                              scope=scope, as_neighbor=k_as)
+                                              scope=scope, as_neighbor=k_as, prefetch_next=nxt)
         levels.append((xyz, points))
     end_points["l1_xyz"] = levels[0][0]
     end_points["l2_xyz"] = levels[0][0]   # sic: the reference stores l1_xyz under 'l2_xyz' (:38)

@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _ops, tf_util
-from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss, index_cache
+from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss, index_cache, prefetch_neighbourhood
 from ..pointnet_util import pointnet_fp_module
 from .pointasnl_cls import l2_on_weights
 
@@ -16,9 +16,9 @@ def placeholder_inputs(batch_size, num_point, feature_channel=0, device="cuda"):
             torch.zeros((batch_size, num_point), device=device))
 
 
-def _sa(xyz, feat, npoint, mlp, scope, k_as, nl, cfg):
+def _sa(xyz, feat, npoint, mlp, scope, k_as, nl, cfg, prefetch_next=None):
     return PointASNLSetAbstraction(xyz, feat, npoint=npoint, nsample=32, mlp=mlp, scope=scope, as_neighbor=k_as,
-                                   NL=nl, **cfg)
+                                   NL=nl, prefetch_next=prefetch_next, **cfg)
 
 
 def get_model(point_cloud, is_training, num_class, bn_decay=None, weight_decay=None, feature_channel=0):
@@ -41,15 +41,17 @@ def _get_model(point_cloud, is_training, num_class, bn_decay, weight_decay, feat
     cfg = dict(is_training=is_training, bn_decay=bn_decay, weight_decay=weight_decay)
     n1, n2, n3, n4 = num_point // 8, num_point // 32, num_point // 128, num_point // 256
 
+    # layer1_1 / layer1_2's FPS + k-NN depend on l0_xyz only: started now, they run beside layer 0
+    prefetch_neighbourhood(l0_xyz, n1, 32)
     _, l0_points = _sa(l0_xyz, l0_points, num_point, [16, 16, 32], "layer0", 0, False, cfg)
     # each residual stage: a sampling layer (FPS + AS + NL) and a same-resolution refinement layer, summed
-    l1_xyz, l1_1 = _sa(l0_xyz, l0_points, n1, [32, 32, 64], "layer1_1", 8, True, cfg)
+    l1_xyz, l1_1 = _sa(l0_xyz, l0_points, n1, [32, 32, 64], "layer1_1", 8, True, cfg, prefetch_next=(n2, 32))
     _, l1_2 = _sa(l0_xyz, l0_points, n1, [64, 64], "layer1_2", 0, False, cfg)
     l1_2 = _ops.add_n(l1_2, l1_1)
-    l2_xyz, l2_1 = _sa(l1_xyz, l1_2, n2, [64, 64, 128], "layer2_1", 4, True, cfg)
+    l2_xyz, l2_1 = _sa(l1_xyz, l1_2, n2, [64, 64, 128], "layer2_1", 4, True, cfg, prefetch_next=(n3, 32))
     _, l2_2 = _sa(l2_xyz, l2_1, n2, [128, 128], "layer2_2", 0, False, cfg)
     l2_2 = _ops.add_n(l2_2, l2_1)
-    l3_xyz, l3_1 = _sa(l2_xyz, l2_2, n3, [128, 128, 256], "layer3_1", 0, True, cfg)
+    l3_xyz, l3_1 = _sa(l2_xyz, l2_2, n3, [128, 128, 256], "layer3_1", 0, True, cfg, prefetch_next=(n4, 32))
     _, l3_2 = _sa(l3_xyz, l3_1, n3, [256, 256], "layer3_2", 0, False, cfg)
     l3_2 = _ops.add_n(l3_2, l3_1)
     l4_xyz, l4_1 = _sa(l3_xyz, l3_1, n4, [256, 256, 512], "layer4_1", 0, True, cfg)   # sic: consumes l3_1 (:50)

@@ -26,15 +26,8 @@ def knn_point(k, xyz1, xyz2):
 
 
 def select_top_k(k, dist):
-    """dist (b, m, n) -> idx (b, m, n) int32, dist_out (b, m, n): the first k entries of each row are the k smallest
-    in ascending order (ascending index among equal distances; selection_sort_gpu's swaps leave ties in a
-    history-dependent order)
-    (reference tf_grouping.py:22-32, tf_grouping_g.cu:83-123); the remaining n-k entries follow in ascending order
-    too (the reference leaves them as an unspecified permutation -- only the first k are documented as useful).
-    Not used by the shipped models; implemented with a stable device sort."""
-    if not (isinstance(dist, torch.Tensor) and dist.is_cuda and dist.dim() == 3):
-        raise ValueError("SelectionSort expects (b,m,n) dist shape.")
-    if int(k) <= 0:
-        raise ValueError("SelectionSort expects positive k")
-    out, idx = torch.sort(dist.float(), dim=-1, stable=True)
-    return idx.to(torch.int32), out
+    """dist (b, m, n) -> idx (b, m, n) int32, dist_out (b, m, n): the first k entries of each row are the k smallest in
+    ascending order; the other n-k entries are the permuted remainder (reference tf_grouping.py:22-32 ->
+    selection_sort_gpu, tf_grouping_g.cu:83-123).  Same "first strict minimum, then swap" rule as the reference, so
+    equal distances and the remainder come out exactly where the reference leaves them.  No gradient."""
+    return _ops.selection_sort(k, dist)

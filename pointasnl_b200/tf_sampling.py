@@ -15,6 +15,7 @@ def gather_point(inp, idx):
 
 
 def prob_sample(inp, inpr):
-    """Reference tf_sampling.py:13-22.  Used only by the reference file's own __main__ demo (SURVEY.md 8a/a12);
-    not on the hot path and not implemented in this revision."""
-    raise NotImplementedError("prob_sample is outside the PointASNL hot path (SURVEY.md section 8a, row a12)")
+    """inp (batch_size, ncategory) float32 non-negative weights, inpr (batch_size, npoints) float32 uniform numbers ->
+    (batch_size, npoints) int32: categories drawn with probability proportional to inp (reference tf_sampling.py:13-22 ->
+    cumsumKernel + binarysearchKernel, tf_sampling_g.cu:7-104).  Same fp32 summation order, hence the same indices."""
+    return _ops.prob_sample(inp, inpr)
