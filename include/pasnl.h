@@ -207,6 +207,14 @@ int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long lda, const 
                        long ldc, double *col_stats, const float *pro_scale, const float *pro_shift, int pro_act,
                        void *stream);
 
+/* The same product for mid-size layers whose operands are TMA-legal (16-byte aligned, lda % 4 == ldw % 4 == 0, k >= 64,
+ * n >= 64, rows >= 2048): both operands streamed by TMA tensor copies, C^T accumulated (csrc/gemm_tma.cu); contractions
+ * of any length (<= 1024-wide slabs summed in fp32), statistics fused for every k.  pasnl_gemm_rows_tf32x3 routes
+ * eligible problems here by itself. */
+int pasnl_gemm_rows_tma_eligible(long rows, int k, int n, const void *A, long lda, const void *Wt, long ldw);
+int pasnl_gemm_rows_tma(long rows, int k, int n, const float *A, long lda, const float *Wt, long ldw, float *C, long ldc,
+                        double *col_stats, void *stream);
+
 /* Weight gradient of the same layers (replaces the tf.matmul / conv2d filter gradients TF autodiff emits):
  *     dW[m, n] = sum_r X[r, m] * Y[r, n] ,   X (rows, m), Y (rows, n), dW (m, n) row-major, ldw == n.
  * X = layer input, Y = gradient w.r.t. the GEMM output.  tcgen05, 3xTF32, operands transposed on the way into shared memory,

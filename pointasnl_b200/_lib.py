@@ -47,6 +47,8 @@ SIGNATURES = {
     "pasnl_gemm_rows_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),
     "pasnl_gemm_rows_ws_eligible": (c_int, [c_long, c_int, c_int, P, c_long]),
     "pasnl_gemm_rows_ws": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, c_int, P, c_long, P, P, P, c_int, P]),
+    "pasnl_gemm_rows_tma_eligible": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long]),
+    "pasnl_gemm_rows_tma": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),
     "pasnl_gemm_wgrad_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, c_int, P]),
     "pasnl_gemm_skinny": (c_int, [c_int, c_int, c_int, P, c_long, P, c_long, c_int, P, c_long, P]),
     "pasnl_wgrad_skinny": (c_int, [c_int, c_int, c_int, P, c_long, P, c_long, P, c_long, P]),

@@ -643,7 +643,8 @@ def gemm_rows(a, w, w_kn=False, col_stats=None):
     bt = transposed_weight(w) if w_kn else w
     # (contractions longer than 1024 run inside the library as side-by-side <= 1024-wide slabs added into a zeroed C:
     #  the TMEM accumulator truncates on every add, ~3e-8 * k relative; statistics are then left to the BN kernel)
-    fuse_stats = col_stats is not None and k <= GEMM_K_SLAB
+    fuse_stats = col_stats is not None and (k <= GEMM_K_SLAB or bool(lib.pasnl_gemm_rows_tma_eligible(
+        rows, k, n, a.data_ptr(), int(a.stride(0)), bt.data_ptr(), int(bt.stride(0)))))
     c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
     _call("pasnl_gemm_rows_tf32x3", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(bt), int(bt.stride(0)), _ptr(c), n,
           _ptr(col_stats) if fuse_stats else None, _stream())

@@ -1372,6 +1372,9 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
     // tall layers whose weights fit one TMEM-resident tile: TMA-fed, weights-stationary kernel (gemm_ws.cu)
     if (pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda))
         return pasnl_gemm_rows_ws(rows, k, n, A, lda, Bt, ldb, 0, C, ldc, col_stats, nullptr, nullptr, 0, stream);
+    // mid-size layers with TMA-legal operands: both operands by TMA, any k (gemm_tma.cu)
+    if (pasnl_gemm_rows_tma_eligible(rows, k, n, A, lda, Bt, ldb))
+        return pasnl_gemm_rows_tma(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, stream);
     // many row tiles per SM and small weights: persistent kernel with the weights resident in shared memory
     // (one launch covers up to 160 output columns, so the 134-wide grouped-feature layers stay single-pass)
     const int kpad = (k + gtc::kKC - 1) / gtc::kKC * gtc::kKC;

@@ -68,3 +68,25 @@ def test_rows_tf32x3_routes_tall_layers_to_ws_and_both_kernels_agree(cuda, monke
     got = _ops.gemm_rows(a, bt)
     want = a.double() @ bt.double().t()
     assert float((got.double() - want).abs().max()) / float(want.abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("rows,k,n", [(16384, 1024, 128), (4096, 256, 4096), (4096, 4096, 256), (5000, 2112, 200),
+                                      (2048, 64, 64), (4097, 100, 130), (16384, 128, 2048), (40960, 128, 64), (3000, 512, 1024)])
+def test_rows_tma_matches_fp64_and_fuses_statistics_for_any_k(cuda, rows, k, n):
+    """csrc/gemm_tma.cu through the routed entry point (pasnl_gemm_rows_tf32x3 -> pasnl_gemm_rows_tma)."""
+    from pointasnl_b200 import _lib, _ops
+    torch.manual_seed(rows + k + n)
+    a = torch.randn(rows, k, device=cuda) * 1.5 + 0.3
+    bt = torch.randn(n, k, device=cuda) / k ** 0.5
+    assert _lib.load().pasnl_gemm_rows_tma_eligible(rows, k, n, a.data_ptr(), k, bt.data_ptr(), k) == 1
+    st = torch.zeros(2 * n, dtype=torch.float64, device=cuda)
+    c, fused = _ops.gemm_rows(a, bt, col_stats=st)
+    assert fused
+    want = a.double() @ bt.double().t()
+    scale = float(want.abs().max())
+    err = float((c.double() - want).abs().max()) / scale
+    print(f"   rows={rows} k={k} n={n}: max error {err:.2e} of the largest output")
+    assert err <= max(3e-6, 3e-8 * min(k, 1024))
+    cd = c.double()
+    torch.testing.assert_close(st[:n], cd.sum(0), rtol=1e-7, atol=2e-7 * scale * rows)
+    torch.testing.assert_close(st[n:], (cd * cd).sum(0), rtol=1e-6, atol=1e-9)
