@@ -322,7 +322,13 @@ extern "C" int pasnl_gemm_rows_tma_eligible(long rows, int k, int n, const void 
     if ((lda % 4) != 0 || (ldw % 4) != 0 || (reinterpret_cast<uintptr_t>(A) & 15u) != 0 ||
         (reinterpret_cast<uintptr_t>(Wt) & 15u) != 0)
         return 0;
-    if (k < 64 || n < 64 || rows < 2048 || rows >= 2147483647L - 128) return 0;
+    if (n < 64 || rows < 2048 || rows >= 2147483647L - 128) return 0;
+    // measured on B200 (tools/sweep_small_gemm.py, profiles/r02_sweep_mid_gemm.json): the TMA pipeline pays off for long
+    // contractions with enough (row tile, channel tile) pairs to cover the SMs -- 16384x1024x128: 45 vs 66 us,
+    // 4096x1024x512: 45 vs 64 us; short k or few tiles stay on the one-tile kernel (its split-k fills the GPU better:
+    // 4096x4096x256: 99 vs 170 us; 16384x128x2048: 113 vs 141 us)
+    const long tiles = ((rows + 127) / 128) * ((n + 127) / 128);
+    if (k < 512 || tiles < (long)gtma::sm_count() * 2 / 3) return 0;
     return 1;
 }
 
