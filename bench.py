@@ -508,7 +508,8 @@ def main():
     prof_steps = min(args.steps, 5)
     ts_prof = ts if args.no_graph else None
     if ts_prof is None:
-        ts_prof = TrainStep(wl["model"], batch, points, dev, adaptive_sample=args.AS, use_graph=False, seed=0, **wl["kw"])
+        ts_prof = TrainStep(wl["model"], batch, points, dev, adaptive_sample=args.AS, use_graph=False, seed=0,
+                            overlap_allreduce=False, **wl["kw"])
         ts_prof.bucket.all_reduce_sum = lambda *a, **k: None    # rank-0 only pass: no collective
         ts_prof.set_inputs(h_pc, h_lab, h_w)
         for _ in range(2):
@@ -578,7 +579,10 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {**config, "l2": "flushed (256 MiB memset) before every timed step, outside the event pair",
-                       "launch": "eager" if args.no_graph else "CUDA graphs (fwd+bwd, Adam) around one NCCL all-reduce"},
+                       "launch": "eager" if args.no_graph else (
+                           "one CUDA graph per step; the gradient all-reduce runs in two pieces, the first one overlapped "
+                           "with the early layers' backward" if getattr(ts, "g_all", None) is not None else
+                           "CUDA graphs (fwd+bwd, optimizer) around one NCCL all-reduce")},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,

@@ -9,7 +9,7 @@ from . import pointasnl_cls, pointasnl_sem_seg_res
 
 class TrainStep:
     def __init__(self, model="cls", batch_size=32, num_point=1024, device="cuda", adaptive_sample=False,
-                 num_class=None, feature_channel=3, lr=1e-3, seed=0, use_graph=False, radius=0.07):
+                 num_class=None, feature_channel=3, lr=1e-3, seed=0, use_graph=False, radius=0.07, overlap_allreduce=True):
         """model: 'cls' (models/pointasnl_cls.py) or 'seg' (models/pointasnl_sem_seg_res.py; feature_channel=3, radius=0.07
         is the ScanNet configuration, feature_channel=1, num_class=20, radius=0.2 the SemanticKITTI one,
         SemanticKITTI/train_semantic_kitti.py:81, train_semantic_kitti_grid.py:144)."""
@@ -70,6 +70,27 @@ class TrainStep:
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None
+        # data parallel: the gradient bucket is all-reduced in two pieces.  Backward visits the layers in reverse creation
+        # order, so the gradients of the LATER ~65 % of the bucket are complete long before the first layers' are: a
+        # multi-grad hook ships that piece (async NCCL all-reduce) while the early layers' backward is still running.
+        self.overlap_allreduce = bool(overlap_allreduce)
+        total, acc, self.split = self.bucket.numel, 0, 0
+        for i, prm in enumerate(self.bucket.params):
+            if acc >= 0.35 * total:
+                self.split = i
+                break
+            acc += prm.numel()
+        self.split_off = self.bucket.offset_of(self.split)
+        self._works = []
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _ship_late_gradients(self, grads):
+        import torch.distributed as dist
+        self.bucket.pack_grads(self.split, grads)
+        self._works.append(dist.all_reduce(self.bucket.flat[self.split_off:], op=dist.ReduceOp.SUM, async_op=True))
 
     def _forward(self, is_training=True, weights_decay=1e-4):
         with self.store.as_default():
@@ -94,13 +115,30 @@ class TrainStep:
         try:
             if self.transposer is not None:
                 self.transposer.refresh()
+            overlap = self.overlap_allreduce and self._world() > 1 and 0 < self.split < len(self.bucket.params)
+            handle = None
             with _ops.use_zero_arena(self.arena):
                 loss = self._forward(weights_decay=0.0)      # the regulariser is folded into the optimizer kernel
+                if overlap:
+                    handle = torch.autograd.graph.register_multi_grad_hook(tuple(self.bucket.params[self.split:]),
+                                                                           self._ship_late_gradients)
                 loss.backward()
+            if handle is not None:
+                handle.remove()
         finally:
             _ops.set_weight_transposer(prev_t)
             _ops.set_dropout_step(prev_d)
-        self.bucket.pack()
+        if overlap and self._works:
+            import torch.distributed as dist
+            self.bucket.pack(0, self.split)
+            self._works.append(dist.all_reduce(self.bucket.flat[:self.split_off], op=dist.ReduceOp.SUM, async_op=True))
+            for w in self._works:
+                w.wait()
+            self._works = []
+            self._reduced = True
+        else:
+            self.bucket.pack()
+            self._reduced = False
         self.data_loss = loss.detach()
 
     def _optimizer_step(self):
@@ -113,11 +151,15 @@ class TrainStep:
 
     def _eager_step(self):
         self._fwd_bwd()
-        self.bucket.all_reduce_sum()
+        if not self._reduced:
+            self.bucket.all_reduce_sum()
         self._optimizer_step()
 
     def capture(self, warmup=3):
-        """Capture fwd+bwd and the optimizer step as two graphs around the (uncaptured) NCCL all-reduce."""
+        """Capture the step.  Single GPU / no overlap: fwd+bwd and the optimizer as two graphs around the (uncaptured)
+        NCCL all-reduce.  Data parallel with overlap: ONE graph holding fwd + bwd + both all-reduce pieces (NCCL is
+        captured on its own stream, forked from the backward) + the optimizer kernel; if NCCL capture is not possible
+        the two-graph form without overlap is used."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -127,6 +169,24 @@ class TrainStep:
         torch.cuda.synchronize()
         from .. import _lib
         c0 = _lib.launch_count
+        self.g_all = None
+        if self.overlap_allreduce and self._world() > 1:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._fwd_bwd()
+                    self._optimizer_step()
+                self.g_all = g
+                self.launches_per_step = _lib.launch_count - c0
+                self.graph = True
+                return
+            except Exception as e:       # NCCL not capturable in this environment: fall back, loudly
+                import sys
+                print(f"[pasnl] all-reduce overlap disabled (graph capture of NCCL failed: {e!r})", file=sys.stderr)
+                self.overlap_allreduce = False
+                self._works = []
+                torch.cuda.synchronize()
+                c0 = _lib.launch_count
         self.g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fb):
             self._fwd_bwd()
@@ -144,7 +204,9 @@ class TrainStep:
             self.smpw.copy_(smpw, non_blocking=non_blocking)
 
     def step(self):
-        if self.graph:
+        if self.graph and getattr(self, "g_all", None) is not None:
+            self.g_all.replay()
+        elif self.graph:
             self.g_fb.replay()
             self.bucket.all_reduce_sum()
             self.g_opt.replay()

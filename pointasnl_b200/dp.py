@@ -42,15 +42,31 @@ class FlatGradBucket:
         for p in self.params:
             p.grad = None
 
-    def pack(self):
-        """Copy the freshly produced gradients into the bucket with one multi-tensor copy and re-alias ``p.grad``."""
-        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+    def pack(self, start=0, stop=None):
+        """Copy the freshly produced gradients of params[start:stop] into the bucket with one multi-tensor copy and
+        re-alias every ``p.grad``."""
+        sel = list(zip(self.views, self.params))[start:stop]
+        have = [(v, p.grad) for v, p in sel if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-        for v, p in zip(self.views, self.params):
+        for v, p in sel:
             if p.grad is None:
                 v.zero_()     # parameter not reached by this step's loss
         self.alias()
+
+    def pack_grads(self, start, grads):
+        """Copy `grads` (as handed to an autograd multi-grad hook: one per params[start:], None = not reached) into the
+        bucket.  Used to ship the late layers' gradients while the early layers' backward is still running."""
+        views = self.views[start:start + len(grads)]
+        have = [(v, g) for v, g in zip(views, grads) if g is not None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v, g in zip(views, grads):
+            if g is None:
+                v.zero_()
+
+    def offset_of(self, index):
+        return sum(p.numel() for p in self.params[:index])
 
     def check_aliasing(self):
         """autograd must have accumulated in place (it does when .grad is pre-populated); guard against a silent
