@@ -498,9 +498,19 @@ def main():
     e2e_value = global_batch * args.steps / e2e_total
     h2d = h_pc.numel() * 4 + h_lab.numel() * 8 + (h_w.numel() * 4 if h_w is not None else 0)
 
+    if world > 1:
+        # every rank leaves the process group TOGETHER, and before rank 0's single-process passes: the captured graphs
+        # (which hold NCCL kernels) are released first
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        launch_mode_single_graph = getattr(ts, "g_all", None) is not None
+        ts.g_all = ts.g_fb = ts.g_opt = None
+        ts.graph = None
+        torch.cuda.synchronize()
+        torch.distributed.destroy_process_group()
+    else:
+        launch_mode_single_graph = False
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
         return
 
     # ---- per-kernel pass (eager, CUDA events around each pasnl launch) -> roofline of the dominant kernel
@@ -581,15 +591,13 @@ def main():
             "config": {**config, "l2": "flushed (256 MiB memset) before every timed step, outside the event pair",
                        "launch": "eager" if args.no_graph else (
                            "one CUDA graph per step; the gradient all-reduce runs in two pieces, the first one overlapped "
-                           "with the early layers' backward" if getattr(ts, "g_all", None) is not None else
+                           "with the early layers' backward" if launch_mode_single_graph else
                            "CUDA graphs (fwd+bwd, optimizer) around one NCCL all-reduce")},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

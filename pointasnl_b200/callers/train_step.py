@@ -73,7 +73,8 @@ class TrainStep:
         # data parallel: the gradient bucket is all-reduced in two pieces.  Backward visits the layers in reverse creation
         # order, so the gradients of the LATER ~65 % of the bucket are complete long before the first layers' are: a
         # multi-grad hook ships that piece (async NCCL all-reduce) while the early layers' backward is still running.
-        self.overlap_allreduce = bool(overlap_allreduce)
+        import os
+        self.overlap_allreduce = bool(overlap_allreduce) and os.environ.get("PASNL_DP_OVERLAP", "1")[:1] != "0"
         total, acc, self.split = self.bucket.numel, 0, 0
         for i, prm in enumerate(self.bucket.params):
             if acc >= 0.35 * total:
