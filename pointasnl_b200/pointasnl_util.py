@@ -214,9 +214,8 @@ def PointNonLocalCell(feature, new_point, mlp, is_training, bn_decay, weight_dec
     """feature (B, ndataset, C), new_point (B, npoint, nsample, Cq) -> (B, npoint*nsample..., mlp[-1]) exactly as the
     reference shapes it (reference :175-219; the SA layer calls it with new_point = (B, 1, npoint, Cq)).
     The attention map is never materialised: softmax(QK^T)V is one flash-style kernel."""
-    if mode != "dot":
-        raise NotImplementedError("only mode='dot' (the one every shipped model uses) is on the hot path; "
-                                  "mode='concat' materialises a (B, npoint, ndataset, 2D) tensor by construction")
+    if mode not in ("dot", "concat"):
+        raise ValueError("mode must be 'dot' or 'concat'")
     with tf_util.variable_scope(scope):
         bottleneck_channel = mlp[0]
         batch_size, npoint, nsample, _ = new_point.shape
@@ -228,6 +227,12 @@ def PointNonLocalCell(feature, new_point, mlp, is_training, bn_decay, weight_dec
                            activation_fn=None)
         q = q.reshape(batch_size, npoint * nsample, bottleneck_channel)
         kv = kv.squeeze(2)
+        if mode == "concat":
+            out = _concat_attention(q, kv, bottleneck_channel, is_training, bn_decay, weight_decay, bn)
+            out = tf_util.conv2d(out.reshape(batch_size, npoint, nsample, bottleneck_channel), mlp[-1], [1, 1],
+                                 padding="VALID", stride=[1, 1], bn=bn, is_training=is_training,
+                                 scope="conv_back_project", bn_decay=bn_decay, weight_decay=weight_decay)
+            return out.squeeze(1)
         scale = 1.0 / math.sqrt(float(bottleneck_channel)) if scaled else 1.0
         d = bottleneck_channel
         if d % 4:   # the kernel wants a multiple of 4: zero columns change neither q.k nor the kept part of A.v
@@ -240,6 +245,26 @@ def PointNonLocalCell(feature, new_point, mlp, is_training, bn_decay, weight_dec
                              stride=[1, 1], bn=bn, is_training=is_training, scope="conv_back_project",
                              bn_decay=bn_decay, weight_decay=weight_decay)
         return out.squeeze(1)
+
+
+def _concat_attention(q, kv, d, is_training, bn_decay, weight_decay, bn):
+    """mode='concat' (reference :201-209; no shipped model uses it): attention_map[b,i,j] = relu(bn(w . [k_j | q_i] + c)),
+    a 1x1 conv with ONE output channel over the tiled / concatenated (B, S, N, 2D) tensor.  The conv is linear, so the
+    map is a_j + b_i with a = K w[:D], b = Q w[D:]: the 2D-wide tensor of the reference is never built; the (B, S, N)
+    map itself is materialised (plain PyTorch ops: this mode is off the hot path), batch-norm statistics over all its
+    B*S*N entries as tf.contrib.layers.batch_norm takes them for a one-channel NHWC tensor."""
+    store = tf_util.get_default_store()
+    kf, v = kv[..., :d], kv[..., d:]
+    with tf_util.variable_scope("conv_attention_map"):
+        w = tf_util._weights((1, 1, 2 * d, 1), 2 * d, 1, True, 1e-3, weight_decay)
+        bias = store.get_variable("biases", (1,), tf_util.constant_init(0.0))
+        a = torch.matmul(kf, w.view(2 * d, 1)[:d]).squeeze(-1)            # (B, N)
+        b = torch.matmul(q, w.view(2 * d, 1)[d:]).squeeze(-1)             # (B, S)
+        amap = (b.unsqueeze(2) + a.unsqueeze(1) + bias).unsqueeze(-1)      # (B, S, N, 1)
+        if bn:
+            amap = tf_util.batch_norm_for_conv2d(amap, is_training, bn_decay, "bn")
+        amap = torch.relu(amap).squeeze(-1)
+    return torch.matmul(torch.softmax(amap, dim=-1), v)
 
 
 # ---------------------------------------------------------------------------------------------- SA layer

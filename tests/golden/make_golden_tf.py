@@ -85,6 +85,21 @@ def case_nonlocal():
                                    **grad_digests(y, named), **moving()})
 
 
+def case_nonlocal_concat():
+    tf_shim.install()
+    import pointasnl_util as R
+    rng = np.random.default_rng(18)
+    feature = rng.normal(size=(2, 48, 12)).astype(np.float32)
+    new_point = rng.normal(size=(2, 1, 20, 15)).astype(np.float32)
+    f_t = tf_shim.tensor(feature).requires_grad_(True)
+    p_t = tf_shim.tensor(new_point).requires_grad_(True)
+    out = R.PointNonLocalCell(f_t, p_t, [32, 24], True, 0.9, None, "nlc", True, mode="concat")
+    y = probe(out, "nlc/out")
+    named = dict(trainables(), **{"in/feature": f_t, "in/new_point": p_t})
+    save("tf_graph_nonlocal_concat.npz", {"feature": feature, "new_point": new_point, "out": out.detach().numpy(),
+                                          **grad_digests(y, named), **moving()})
+
+
 def case_set_abstraction():
     blob = {}
     rng = np.random.default_rng(13)
@@ -210,7 +225,7 @@ def case_seg():
     save("tf_graph_seg.npz", blob)
 
 
-CASES = {"as": case_adaptive_sampling, "nl": case_nonlocal, "sa": case_set_abstraction, "fp": case_fp_module,
+CASES = {"as": case_adaptive_sampling, "nl": case_nonlocal, "nlc": case_nonlocal_concat, "sa": case_set_abstraction, "fp": case_fp_module,
          "dec": case_decoding_layer, "rep": case_repulsion, "cls": case_cls, "seg": case_seg}
 
 if __name__ == "__main__":

@@ -227,3 +227,16 @@ def test_seg_res_model_vs_reference_python(cuda, tag, fc, ncls, radius):
     # norm against this fp64 reference run (0.58 x the 2 % bar, layer1_1 / layer2_1 conv_query_ds), so the 322 tensors
     # of the deep seg net are held to 5 %
     check_grads(g, tag + "/", {n: v for n, v in store.variables().items() if v.requires_grad}, tol=5e-2)
+
+
+def test_nonlocal_cell_concat_mode_vs_reference_python(cuda):
+    """PointNonLocalCell(mode='concat') (reference pointasnl_util.py:201-209; used by no shipped model)."""
+    from pointasnl_b200.pointasnl_util import PointNonLocalCell
+    g = load("tf_graph_nonlocal_concat.npz")
+    store = new_store(cuda)
+    f, p = dev(g["feature"], cuda, True), dev(g["new_point"], cuda, True)
+    with store.as_default():
+        out = PointNonLocalCell(f, p, [32, 24], True, 0.9, None, "nlc", True, mode="concat")
+    close(out, g["out"], 5e-4, "out")
+    probe(out, "nlc/out").backward()
+    check_grads(g, "", named_with_inputs(store, feature=f, new_point=p))

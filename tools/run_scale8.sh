@@ -1,0 +1,21 @@
+#!/bin/bash
+# 8-GPU lines for every BASELINE config (weak scaling) + strong scaling of config 2.  Run under gpurun --gpus 8.
+mkdir -p gpurun_out
+run() {  # name, gpus, flags...
+  name=$1; g=$2; shift 2
+  if [ "$g" = 1 ]; then
+    timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline "$@" > gpurun_out/scale_${name}_n$g.json 2> gpurun_out/scale_${name}_n$g.err
+  else
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $g --steps 20 --warmup 5 --no-cpu-baseline "$@" > gpurun_out/scale_${name}_n$g.json 2> gpurun_out/scale_${name}_n$g.err
+  fi
+  echo "$name n=$g rc=$? $(cut -c1-170 gpurun_out/scale_${name}_n$g.json | tail -1)"
+}
+run cls 8
+run clsAS 8 --AS
+run seg 8 --workload seg
+run kitti 8 --workload kitti
+run cls_strong 8 --scaling strong --batch 32
+run clsAS_strong 8 --AS --scaling strong --batch 32
+run seg 4 --workload seg
+run seg 2 --workload seg
+run cls 4
