@@ -222,6 +222,13 @@ int pasnl_gemm_rows_tma(long rows, int k, int n, const float *A, long lda, const
  * here unless dw_zeroed != 0 (the caller passes memory that is already all-zero, e.g. a slice of a per-step arena). */
 int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
                             long ldw, int dw_zeroed, void *stream);
+/* The same weight gradient with both operands streamed by TMA as MN-major tiles (SWIZZLE_128B with 32-byte atomicity: no
+ * transposes, csrc/gemm_wgrad_tma.cu).  Needs 16-byte aligned operands with ldx % 4 == ldy % 4 == 0, m, n >= 32,
+ * rows >= 2048; pasnl_gemm_wgrad_tf32x3 routes eligible problems here by itself. */
+int pasnl_gemm_wgrad_tma_eligible(long rows, int m, int n, const void *X, long ldx, const void *Y, long ldy);
+int pasnl_gemm_wgrad_tma(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW, long ldw,
+                         int dw_zeroed, void *stream);
+
 
 /* ---------------------------------------------------------------- launch-bound glue of a training step (csrc/small_ops.cu)
  * The callers' classifier head, residual adds, channel concats, dropout, losses and optimizer as library kernels, so

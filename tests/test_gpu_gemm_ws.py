@@ -90,3 +90,22 @@ def test_rows_tma_matches_fp64_and_fuses_statistics_for_any_k(cuda, rows, k, n):
     cd = c.double()
     torch.testing.assert_close(st[:n], cd.sum(0), rtol=1e-7, atol=2e-7 * scale * rows)
     torch.testing.assert_close(st[n:], (cd * cd).sum(0), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("rows,m,n", [(4096, 128, 128), (262144, 128, 128), (524288, 64, 64), (16384, 2048, 128),
+                                      (4096, 256, 4096), (5001, 100, 72), (2048, 32, 32), (70000, 132, 96), (9999, 260, 40)])
+def test_wgrad_tma_mn_major_matches_fp64(cuda, rows, m, n):
+    """csrc/gemm_wgrad_tma.cu: dW = X^T Y with both operands as MN-major TMA tiles (SWIZZLE_128B, 32-byte atoms)."""
+    from pointasnl_b200 import _lib, _ops
+    torch.manual_seed(rows + m + n)
+    x = torch.randn(rows, m, device=cuda) * 1.2 + 0.1
+    dy = torch.randn(rows, n, device=cuda)
+    assert _lib.load().pasnl_gemm_wgrad_tma_eligible(rows, m, n, x.data_ptr(), m, dy.data_ptr(), n) == 1
+    dw = torch.empty(m, n, device=cuda)
+    _lib.call("pasnl_gemm_wgrad_tma", rows, m, n, x.data_ptr(), m, dy.data_ptr(), n, dw.data_ptr(), n, 0, _ops._stream())
+    want = x.double().t() @ dy.double()
+    err = float((dw.double() - want).abs().max()) / float(want.abs().max())
+    print(f"   rows={rows} m={m} n={n}: max error {err:.2e} of the largest entry")
+    assert err < 2e-5
+    routed = _ops.gemm_wgrad(x, dy)
+    assert float((routed.double() - want).abs().max()) / float(want.abs().max()) < 2e-5
