@@ -9,8 +9,9 @@
 // (UMMA layout type SWIZZLE_128B_BASE32B), which is exactly what a TMA tensor copy with
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes: a box of 32 columns x 32 rows lands as 32 rows of 128 bytes, 4-row atoms
 // of 512 bytes.  So here nothing is transposed and no thread touches an address:
-//   TMA warp    per stage (32 contraction rows): 4 boxes of X (128 columns), n/32 boxes of Y  -> 16 + 16 KB
-//   makers      lo = x - tf32(x) for both tiles, element-wise, layout-agnostic
+//   TMA warp    per stage (32 contraction rows): 4 boxes of X (128 columns), n/32 boxes of Y  -> 16 + 16 KB, into a
+//               4-deep RAW ring (three stages of loads in flight: the tall layers are bound by load latency)
+//   makers      tf32(x) in place, lo = x - tf32(x) into a 2-deep lo ring, element-wise, layout-agnostic
 //   MMA warp    4 k-steps (8 rows) x (Xhi.Yhi, Xlo.Yhi, Xhi.Ylo); descriptors: start + 1024 B per k-step,
 //               LBO = 4096 B between 32-column chunks, SBO = 512 B between 4-row atoms, a_major = b_major = MN
 //   epilogue    every 1024 contraction rows the accumulator (the TMEM adder truncates) is added into dW with red.add,
@@ -120,7 +121,9 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
 constexpr int kKRows = 32;                       // contraction rows per stage
 constexpr int kChunkBytes = kKRows * 128;        // one 32-column x 32-row box: 4 KB
 constexpr int kOpBytes = 4 * kChunkBytes;        // 128 columns: 16 KB
-constexpr int kStage4 = 4 * kOpBytes;            // X hi | X lo | Y hi | Y lo
+constexpr int kRawStage = 2 * kOpBytes;          // X | Y as the TMA writes them (tf32(x) in place after the makers): 32 KB
+constexpr int kRaw = 4;                          // raw ring: up to 3 stages of loads in flight while one is consumed
+constexpr int kLo = 2;                           // lo ring (X lo | Y lo, 32 KB): only stages in the maker / MMA phase need one
 constexpr int kSubStages = 32;                   // 32 x 32 = 1024 rows per accumulation
 
 __host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {   // kind::tf32, fp32 accumulate, MN-major A and B
@@ -141,10 +144,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap, long rows, long slab,
                       int m, int n, int nq, float *__restrict__ dW, long ldw) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t loaded[kStages], ready[kStages], empty[kStages], tfull[2], tempty[2];
+    __shared__ uint64_t loaded[kRaw], empty[kRaw], ready[kLo], lofree[kLo], tfull[2], tempty[2];
     __shared__ uint32_t tmem_slot;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     uint8_t *stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *lobuf = stages + (size_t)kRaw * kRawStage;
     const int m0 = blockIdx.y * 128, n0 = blockIdx.z * nq;
     const long r_begin = (long)blockIdx.x * slab, r_end = min(rows, r_begin + slab);
     if (r_begin >= r_end) return;
@@ -153,7 +157,8 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_con
     const int ychunks = nq / 32;
 
     if (t == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&loaded[s], 1); mbar_init(&ready[s], kMakerWarps); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kRaw; ++s) { mbar_init(&loaded[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kLo; ++s) { mbar_init(&ready[s], kMakerWarps); mbar_init(&lofree[s], 1); }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
         mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
         fence_mbar_init();
@@ -176,28 +181,27 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_con
                 const int r0 = (int)(r_begin + (long)i * kKRows);
                 mbar_wait(&empty[s], par);
                 mbar_expect_tx(&loaded[s], (uint32_t)(4 + ychunks) * kChunkBytes);
-                uint8_t *st = stages + (size_t)s * kStage4;
+                uint8_t *st = stages + (size_t)s * kRawStage;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tma_load_2d(st + c * kChunkBytes, &xmap, m0 + 32 * c, r0, &loaded[s]);
-                for (int c = 0; c < ychunks; ++c) tma_load_2d(st + 2 * kOpBytes + c * kChunkBytes, &ymap, n0 + 32 * c, r0, &loaded[s]);
-                if (++s == kStages) { s = 0; par ^= 1u; }
+                for (int c = 0; c < ychunks; ++c) tma_load_2d(st + kOpBytes + c * kChunkBytes, &ymap, n0 + 32 * c, r0, &loaded[s]);
+                if (++s == kRaw) { s = 0; par ^= 1u; }
             }
         }
     } else if (warp == kMmaWarp) {
         const uint32_t idesc = make_idesc_mn(128, nq);
         int s = 0;
-        uint32_t par = 0;
         for (int i = 0; i < nst; ++i) {
-            const int sub = i / kSubStages, ci = i - sub * kSubStages, b = sub & 1;
+            const int sub = i / kSubStages, ci = i - sub * kSubStages, b = sub & 1, l = i & 1;
             if (ci == 0) {
                 mbar_wait(&tempty[b], (uint32_t)(((sub >> 1) & 1) ^ 1));
                 tc_fence_after();
             }
-            mbar_wait(&ready[s], par);
+            mbar_wait(&ready[l], (uint32_t)((i >> 1) & 1));
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t x_hi = smem_u32(stages + (size_t)s * kStage4), x_lo = x_hi + kOpBytes;
-                const uint32_t y_hi = x_hi + 2 * kOpBytes, y_lo = y_hi + kOpBytes;
+                const uint32_t x_hi = smem_u32(stages + (size_t)s * kRawStage), y_hi = x_hi + kOpBytes;
+                const uint32_t x_lo = smem_u32(lobuf + (size_t)l * kRawStage), y_lo = x_lo + kOpBytes;
                 const uint32_t d = tmem + b * 128;
 #pragma unroll
                 for (int ks = 0; ks < kKRows / 8; ++ks) {
@@ -208,21 +212,24 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_con
                     mma_tf32_ss(d, xh, yl, idesc, 1);
                 }
                 mma_commit(&empty[s]);
+                mma_commit(&lofree[l]);
                 if (ci == kSubStages - 1 || i == nst - 1) mma_commit(&tfull[b]);
             }
             __syncwarp();
-            if (++s == kStages) { s = 0; par ^= 1u; }
+            if (++s == kRaw) s = 0;
         }
     } else if (warp >= kMakerWarp0) {
         const int mt = t - kMakerWarp0 * 32;
         int s = 0;
         uint32_t par = 0;
         for (int i = 0; i < nst; ++i) {
+            const int l = i & 1;
             mbar_wait(&loaded[s], par);
+            mbar_wait(&lofree[l], (uint32_t)(((i >> 1) & 1) ^ 1));         // lo slot l was read by the MMAs of stage i - 2
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                float4 *hi = reinterpret_cast<float4 *>(stages + (size_t)s * kStage4 + half * 2 * kOpBytes) + mt;
-                float4 *lo = hi + kOpBytes / 16;
+                float4 *hi = reinterpret_cast<float4 *>(stages + (size_t)s * kRawStage + half * kOpBytes) + mt;
+                float4 *lo = reinterpret_cast<float4 *>(lobuf + (size_t)l * kRawStage + half * kOpBytes) + mt;
                 const int pieces = half == 0 ? 4 : ychunks;            // 256 threads x 16 B = one 4 KB chunk per pass
                 for (int p = 0; p < pieces; ++p) {
                     const float4 v = hi[256 * p];
@@ -235,8 +242,8 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_con
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ready[s]);
-            if (++s == kStages) { s = 0; par ^= 1u; }
+            if (lane == 0) mbar_arrive(&ready[l]);
+            if (++s == kRaw) { s = 0; par ^= 1u; }
         }
     } else {
         // epilogue: lane = row of dW (m index): add finished 1024-row partial sums into dW
@@ -345,7 +352,7 @@ extern "C" int pasnl_gemm_wgrad_tma(long rows, int m, int n, const float *X, lon
     slab = (slab + gwt::kKRows - 1) / gwt::kKRows * gwt::kKRows;
     const long slabs = (rows + slab - 1) / slab;
     const dim3 grid((unsigned)slabs, (unsigned)mt, (unsigned)ntl);
-    const size_t smem = (size_t)gwt::kStages * gwt::kStage4 + 1024;
+    const size_t smem = (size_t)(gwt::kRaw + gwt::kLo) * gwt::kRawStage + 1024;
     cudaError_t e = cudaFuncSetAttribute(gwt::gemm_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     gwt::gemm_wgrad_tma_kernel<<<grid, gwt::kThreads, smem, st>>>(xmap, ymap, rows, slab, m, n, nq, dW, ldw);
