@@ -35,14 +35,14 @@ def _rows_ws2():
     return lambda: _ops.gemm_rows(a, w, w_kn=True, col_stats=st)
 
 
-@op("wgrad_262144x128x128", "pasnl_gemm_wgrad_tf32x3", [262144, 128, 128], "gemm_wgrad_tm_kernel")
+@op("wgrad_262144x128x128", "pasnl_gemm_wgrad_tf32x3", [262144, 128, 128], "gemm_wgrad_tma_kernel")
 def _wgrad():
     x = torch.randn(262144, 128, device="cuda")
     dy = torch.randn(262144, 128, device="cuda")
     return lambda: _ops.gemm_wgrad(x, dy)
 
 
-@op("rows_16384x1024x128", "pasnl_gemm_rows_tf32x3", [16384, 1024, 128], "gemm_rows_kernel")
+@op("rows_16384x1024x128", "pasnl_gemm_rows_tf32x3", [16384, 1024, 128], "gemm_rows_tma_kernel")
 def _rows_mid():
     a = torch.randn(16384, 1024, device="cuda")
     bt = torch.randn(128, 1024, device="cuda") / 32

@@ -17,7 +17,10 @@ METRICS = {"dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "
            "gpu__time_duration.sum": "duration_ns", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_pct",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_pct",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
-           "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct", "launch__registers_per_thread": "registers"}
+           "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct", "launch__registers_per_thread": "registers",
+           "sm__inst_executed_pipe_tensor.sum": "tensor_insts", "smsp__cycles_active.avg": "smsp_cycles_active",
+           "l1tex__data_bank_conflicts_pipe_lsu.sum": "lsu_bank_conflicts",
+           "smsp__inst_executed.sum": "inst_executed", "sm__cycles_elapsed.max": "sm_cycles"}
 UNIT_SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3,
               "msecond": 1e6}
 
