@@ -640,6 +640,18 @@ def gemm_rows(a, w, w_kn=False, col_stats=None):
         _call("pasnl_gemm_rows_ws", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(w), int(w.stride(0)), 1 if w_kn else 0,
               _ptr(c), n, _ptr(col_stats), None, None, 0, _stream())
         return c if col_stats is None else (c, True)
+    if (col_stats is None and not w_kn and 128 < n <= 160
+            and lib.pasnl_gemm_rows_ws_eligible(rows, k, 128, a.data_ptr(), int(a.stride(0)))):
+        # a tall input-gradient product with a few more than 128 output columns (the 134-wide grouped tensor of cls
+        # layer 2): 128 columns through the weights-stationary kernel, the remainder through the one-tile kernel, both
+        # writing their column range of the same C
+        c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
+        _call("pasnl_gemm_rows_ws", rows, k, 128, _ptr(a), int(a.stride(0)), _ptr(w), int(w.stride(0)), 0, _ptr(c), n,
+              None, None, None, 0, _stream())
+        rest = w[128:]
+        _call("pasnl_gemm_rows_tf32x3", rows, k, n - 128, _ptr(a), int(a.stride(0)), rest.data_ptr(), int(w.stride(0)),
+              c.data_ptr() + 4 * 128, n, None, _stream())
+        return c
     bt = transposed_weight(w) if w_kn else w
     # (contractions longer than 1024 run inside the library as side-by-side <= 1024-wide slabs added into a zeroed C:
     #  the TMEM accumulator truncates on every add, ~3e-8 * k relative; statistics are then left to the BN kernel)

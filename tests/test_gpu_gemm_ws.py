@@ -109,3 +109,14 @@ def test_wgrad_tma_mn_major_matches_fp64(cuda, rows, m, n):
     assert err < 2e-5
     routed = _ops.gemm_wgrad(x, dy)
     assert float((routed.double() - want).abs().max()) / float(want.abs().max()) < 2e-5
+
+
+def test_tall_dgrad_with_134_columns_splits_onto_the_ws_kernel(cuda):
+    from pointasnl_b200 import _ops
+    torch.manual_seed(9)
+    dy = torch.randn(262144, 128, device=cuda)
+    w = torch.randn(134, 128, device=cuda) / 11          # stored [cin=134][cout=128] = the [n][k] view of dx = dy . W^T
+    dx = _ops.gemm_rows(dy, w, w_kn=False)
+    want = dy.double() @ w.double().t()
+    assert tuple(dx.shape) == (262144, 134)
+    assert float((dx.double() - want).abs().max()) / float(want.abs().max()) < 5e-6
