@@ -5,7 +5,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _ops, tf_util
-from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss, index_cache
+from ..pointasnl_util import PointASNLSetAbstraction, branch, get_repulsion_loss, index_cache
 from ..pointnet_util import pointnet_sa_module
 
 # (scope, npoint, nsample, mlp) of the two set-abstraction layers, reference :33-36
@@ -41,20 +41,30 @@ def _get_model(point_cloud, is_training, use_normal, bn_decay, weight_decay, num
     as_neighbor = [12, 12] if adaptive_sample else [0, 0]
 
     levels = []
+    pooled = [None, None]
+    head_branch = None
     for li, ((scope, npoint, nsample, mlp), k_as) in enumerate(zip(SA_LAYERS, as_neighbor)):
         nxt = (SA_LAYERS[li + 1][1], SA_LAYERS[li + 1][2]) if li + 1 < len(SA_LAYERS) else None
         xyz, points = PointASNLSetAbstraction(xyz, points, npoint=npoint, nsample=nsample, mlp=mlp,
                                               is_training=is_training, bn_decay=bn_decay, weight_decay=weight_decay,
                                               scope=scope, as_neighbor=k_as, prefetch_next=nxt)
         levels.append((xyz, points))
+        if li == 0:
+            # the global head on (l1_xyz, l1_points) (:39) only needs layer 1: it runs beside layer 2 on a side stream
+            head_branch = branch(xyz, points, slot=2)
+            with head_branch:
+                hs, hm = HEADS[0]
+                _, feat, _ = pointnet_sa_module(xyz, points, npoint=None, radius=None, nsample=None, mlp=hm, mlp2=None,
+                                                group_all=True, is_training=is_training, bn_decay=bn_decay, scope=hs)
+                pooled[0] = feat.reshape(batch_size, -1)
     end_points["l1_xyz"] = levels[0][0]
     end_points["l2_xyz"] = levels[0][0]   # sic: the reference stores l1_xyz under 'l2_xyz' (:38)
 
-    pooled = []
-    for (scope, mlp), (lx, lp) in zip(HEADS, levels):
-        _, feat, _ = pointnet_sa_module(lx, lp, npoint=None, radius=None, nsample=None, mlp=mlp, mlp2=None,
-                                        group_all=True, is_training=is_training, bn_decay=bn_decay, scope=scope)
-        pooled.append(feat.reshape(batch_size, -1))
+    (scope, mlp), (lx, lp) = HEADS[1], levels[1]
+    _, feat, _ = pointnet_sa_module(lx, lp, npoint=None, radius=None, nsample=None, mlp=mlp, mlp2=None,
+                                    group_all=True, is_training=is_training, bn_decay=bn_decay, scope=scope)
+    pooled[1] = feat.reshape(batch_size, -1)
+    head_branch.join(pooled[0])
     net = _ops.concat_cols(pooled[1], pooled[0])          # [l3_points, l3_points_res] (:45)
     net = tf_util.fully_connected(net, 512, bn=True, is_training=is_training, scope="fc1", bn_decay=bn_decay)
     net = tf_util.dropout(net, keep_prob=0.4, is_training=is_training, scope="dp1")

@@ -56,6 +56,52 @@ def _memoized(tag, srcs, extra, fn):
 
 
 _side_streams = {}
+_branch_streams = {}
+
+
+class branch:
+    """``with branch(x, y) as br: z = f(x, y)`` runs f on a side stream that first waits for the current stream (so x, y
+    are ready); ``br.join(z, ...)`` makes the current stream wait for it before z is used.  Independent branches of a
+    layer (the Non-Local cell next to the local cell, the two global heads of the classifier) then overlap instead of
+    queueing behind each other -- most of their kernels are latency-bound and leave SMs idle.  Autograd replays each
+    node's backward on the stream its forward ran on, so the backward branches overlap too.  PASNL_BRANCH_STREAMS=0
+    (or CPU tensors) turns the class into a no-op."""
+    enabled = None
+
+    def __init__(self, *tensors, slot=0):
+        import os
+        if branch.enabled is None:
+            branch.enabled = os.environ.get("PASNL_BRANCH_STREAMS", "1")[:1] != "0"
+        self.active = branch.enabled and bool(tensors) and all(t.is_cuda for t in tensors if t is not None)
+        self.tensors = [t for t in tensors if t is not None]
+        self.slot = slot
+
+    def __enter__(self):
+        if self.active:
+            dev = self.tensors[0].device
+            self.main = torch.cuda.current_stream(dev)
+            key = (dev.index, self.slot)
+            self.side = _branch_streams.get(key)
+            if self.side is None:
+                self.side = _branch_streams[key] = torch.cuda.Stream(dev)
+            self.side.wait_stream(self.main)
+            for t in self.tensors:
+                t.record_stream(self.side)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *outs):
+        if self.active:
+            self.main.wait_stream(self.side)
+            for t in outs:
+                if t is not None:
+                    t.record_stream(self.main)
 
 
 def prefetch_neighbourhood(xyz, npoint, nsample):
@@ -301,10 +347,13 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
             skip_spatial = _ops.MaxPoolK.apply(new_point)
             grouped_xyz = new_point[..., :3]
 
-        if NL:                                                             # reference :252-256
-            new_nonlocal_point = PointNonLocalCell(feature, new_feature.unsqueeze(1),
-                                                   [max(32, num_channel // 2), nl_channel], is_training, bn_decay,
-                                                   weight_decay, scope, bn)
+        nl_branch = None
+        if NL:                                                             # reference :252-256 -- on a side stream
+            nl_branch = branch(feature, new_feature, slot=1)
+            with nl_branch:
+                new_nonlocal_point = PointNonLocalCell(feature, new_feature.unsqueeze(1),
+                                                       [max(32, num_channel // 2), nl_channel], is_training, bn_decay,
+                                                       weight_decay, scope, bn)
         # skip connection (reference :258-262)
         skip_spatial = tf_util.conv1d(skip_spatial, mlp[-1], 1, padding="VALID", stride=1, bn=bn,
                                       is_training=is_training, scope="skip", bn_decay=bn_decay,
@@ -322,6 +371,8 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
                                    bn=bn, is_training=is_training, scope="after_conv", bn_decay=bn_decay,
                                    weight_decay=weight_decay)
         new_point = new_point.squeeze(2)
+        if nl_branch is not None:
+            nl_branch.join(new_nonlocal_point)
         new_point = _ops.add_n(new_point, skip_spatial, new_nonlocal_point if NL else None)
         # feature fusion (reference :287-290)
         new_point = tf_util.conv1d(new_point, mlp[-1], 1, padding="VALID", stride=1, bn=bn, is_training=is_training,
