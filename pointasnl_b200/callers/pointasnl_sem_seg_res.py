@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _ops, tf_util
-from ..pointasnl_util import PointASNLSetAbstraction, get_repulsion_loss, index_cache, prefetch_neighbourhood
+from ..pointasnl_util import PointASNLSetAbstraction, branch, get_repulsion_loss, index_cache, prefetch_neighbourhood
 from ..pointnet_util import pointnet_fp_module
 from .pointasnl_cls import l2_on_weights
 
@@ -45,8 +45,12 @@ def _get_model(point_cloud, is_training, num_class, bn_decay, weight_decay, feat
     prefetch_neighbourhood(l0_xyz, n1, 32)
     _, l0_points = _sa(l0_xyz, l0_points, num_point, [16, 16, 32], "layer0", 0, False, cfg)
     # each residual stage: a sampling layer (FPS + AS + NL) and a same-resolution refinement layer, summed
+    # layer1_2 reads the same inputs as layer1_1 and nothing of it: it runs beside it on a side stream
+    res_branch = branch(l0_xyz, l0_points, slot=3)
+    with res_branch:
+        _, l1_2 = _sa(l0_xyz, l0_points, n1, [64, 64], "layer1_2", 0, False, cfg)
     l1_xyz, l1_1 = _sa(l0_xyz, l0_points, n1, [32, 32, 64], "layer1_1", 8, True, cfg, prefetch_next=(n2, 32))
-    _, l1_2 = _sa(l0_xyz, l0_points, n1, [64, 64], "layer1_2", 0, False, cfg)
+    res_branch.join(l1_2)
     l1_2 = _ops.add_n(l1_2, l1_1)
     l2_xyz, l2_1 = _sa(l1_xyz, l1_2, n2, [64, 64, 128], "layer2_1", 4, True, cfg, prefetch_next=(n3, 32))
     _, l2_2 = _sa(l2_xyz, l2_1, n2, [128, 128], "layer2_2", 0, False, cfg)

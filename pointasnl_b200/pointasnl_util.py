@@ -45,8 +45,8 @@ def _memoized(tag, srcs, extra, fn):
     hit = _memo.get(key)
     if hit is not None and all(h is t for h, t in zip(hit[0], srcs)):
         res = hit[1]
-        ev = _memo.pop(("pending", id(res)), None)
-        if ev is not None:               # produced by prefetch_neighbourhood on the side stream: join before first use
+        ev = _memo.get(("pending", id(res)))
+        if ev is not None:               # produced by prefetch_neighbourhood on a side stream: EVERY consumer stream joins
             torch.cuda.current_stream().wait_event(ev)
             res.record_stream(torch.cuda.current_stream())
         return res
