@@ -80,7 +80,7 @@ class branch:
         if self.active:
             dev = self.tensors[0].device
             self.main = torch.cuda.current_stream(dev)
-            key = (dev.index, self.slot)
+            key = (dev.index, self.slot, self.main.cuda_stream)      # every parent stream has its own children
             self.side = _branch_streams.get(key)
             if self.side is None:
                 self.side = _branch_streams[key] = torch.cuda.Stream(dev)
@@ -355,9 +355,11 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
                                                        [max(32, num_channel // 2), nl_channel], is_training, bn_decay,
                                                        weight_decay, scope, bn)
         # skip connection (reference :258-262)
-        skip_spatial = tf_util.conv1d(skip_spatial, mlp[-1], 1, padding="VALID", stride=1, bn=bn,
-                                      is_training=is_training, scope="skip", bn_decay=bn_decay,
-                                      weight_decay=weight_decay)
+        skip_branch = branch(skip_spatial, slot=4)       # a small layer (rows = B*S): beside the tall local-cell layers
+        with skip_branch:
+            skip_spatial = tf_util.conv1d(skip_spatial, mlp[-1], 1, padding="VALID", stride=1, bn=bn,
+                                          is_training=is_training, scope="skip", bn_decay=bn_decay,
+                                          weight_decay=weight_decay)
         # point local cell (reference :264-280)
         for i, num_out_channel in enumerate(mlp):
             if i != len(mlp) - 1:
@@ -373,6 +375,7 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
         new_point = new_point.squeeze(2)
         if nl_branch is not None:
             nl_branch.join(new_nonlocal_point)
+        skip_branch.join(skip_spatial)
         new_point = _ops.add_n(new_point, skip_spatial, new_nonlocal_point if NL else None)
         # feature fusion (reference :287-290)
         new_point = tf_util.conv1d(new_point, mlp[-1], 1, padding="VALID", stride=1, bn=bn, is_training=is_training,
