@@ -326,18 +326,23 @@ def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0, full_ba
     cores = os.cpu_count() or 1
     # the in-line cpu_baseline leg times a bounded sample; `--impl reference` (full_batch) runs the whole cls batch
     sample_batch = min(batch, 8 if args.workload == "cls" else (2 if args.workload == "seg" else 1))
-    if full_batch and args.workload == "cls":
+    if full_batch:
         sample_batch = batch
-    pc, labels, smpw = make_batch(args.workload, sample_batch, points, 1)
-    x = torch.from_numpy(pc)
-    y = torch.from_numpy(labels)
+    data = {}
+
+    def load(nb):
+        pc, labels, smpw = make_batch(args.workload, nb, points, 1)
+        data["x"], data["y"] = torch.from_numpy(pc), torch.from_numpy(labels)
+        data["w"] = torch.from_numpy(smpw) if smpw is not None else None
+
+    load(sample_batch)
     r = model_ref.Ref(None, dtype=torch.float32, dropout=True, native_knn=True, native_interp=True)
 
     def fwd():
         if args.workload == "cls":
-            return model_ref.cls_forward(r, x, y, use_normal=True, adaptive_sample=args.AS)[1]
+            return model_ref.cls_forward(r, data["x"], data["y"], use_normal=True, adaptive_sample=args.AS)[1]
         kw = WORKLOADS[args.workload]["kw"]
-        return model_ref.seg_forward(r, x, kw["num_class"], y, torch.from_numpy(smpw),
+        return model_ref.seg_forward(r, data["x"], kw["num_class"], data["y"], data["w"],
                                      feature_channel=kw["feature_channel"], radius=kw["radius"])[1]
 
     torch.set_num_threads(min(cores, 16))
@@ -368,6 +373,11 @@ def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0, full_ba
             break
     threads = best[0]
     torch.set_num_threads(threads)
+    # `--impl reference --steps K --warmup W` runs exactly K + W steps: when that would not fit the time budget at the
+    # full batch, the per-step SAMPLE shrinks (clouds are independent apart from the batch-norm statistics), not K
+    if full_batch and (steps + warmup) * best[1] > budget_s and sample_batch > 2:
+        sample_batch = max(2, int(sample_batch * budget_s / ((steps + warmup) * best[1])))
+        load(sample_batch)
     cref.set_threads(min(threads, sample_batch))
     for _ in range(warmup):
         one_step()
@@ -376,7 +386,7 @@ def run_cpu_reference(args, batch, points, steps, warmup, budget_s=40.0, full_ba
     for _ in range(max(1, steps)):
         one_step()
         done += 1
-        if time.perf_counter() - t0 > budget_s / 2:
+        if not full_batch and time.perf_counter() - t0 > budget_s / 2:
             break
     dt = time.perf_counter() - t0
     kind = "reference" if refnative.available("ref_knn.so") else "port"
@@ -408,18 +418,23 @@ def main():
     workload_name = model_name + (f" B={batch} N={points} per GPU" if args.scaling == "weak" else
                                   f" global B={global_batch} N={points} sharded over {world} GPU(s)") + ", synthetic"
     metric = METRIC if args.workload == "cls" else f"point-clouds/sec fwd+bwd pointasnl_sem_seg_res B={wl['batch']} N={points}"
+    # one protocol description shared by both arms (so that the two JSON lines carry the same `config`)
     config = {"workload": workload_name, "step": "forward + loss + backward + grad all-reduce + Adam",
               "parallelism": f"dp{world}", "global_batch": global_batch,
-              "batch_norm": "per-replica statistics" if world > 1 else "single replica"}
+              "batch_norm": "per-replica statistics" if world > 1 else "single replica",
+              "l2": "GPU arm: flushed (256 MiB memset) before every timed step, outside the event pair",
+              "launch": "GPU arm: CUDA graphs (fwd+bwd, optimizer) around one NCCL all-reduce, or eager with --no-graph; "
+                        "reference arm: host threads"}
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample: a few full steps of the same workload on all host cores
-        steps = max(1, min(args.steps, 3))
-        warm = 0
-        val, ms, threads, kind, sample, cores = run_cpu_reference(args, batch, points, steps, warm, full_batch=True)
+        # exactly --steps / --warmup steps of the same workload on the host cores; the per-step sample is the full batch
+        # when that fits ~3 minutes, a bounded share of it otherwise
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        val, ms, threads, kind, sample, cores = run_cpu_reference(args, batch, points, steps, warm, budget_s=180.0,
+                                                                  full_batch=True)
         line = {"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                 "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
@@ -592,11 +607,10 @@ def main():
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {**config, "l2": "flushed (256 MiB memset) before every timed step, outside the event pair",
-                       "launch": "eager" if args.no_graph else (
-                           "one CUDA graph per step; the gradient all-reduce runs in two pieces, the first one overlapped "
-                           "with the early layers' backward" if launch_mode_single_graph else
-                           "CUDA graphs (fwd+bwd, optimizer) around one NCCL all-reduce")},
+            "config": config,
+            "launch_mode": "eager" if args.no_graph else (
+                "one CUDA graph per step with a two-piece overlapped all-reduce" if launch_mode_single_graph else
+                "CUDA graphs (fwd+bwd, optimizer) around one NCCL all-reduce"),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
