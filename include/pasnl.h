@@ -226,8 +226,11 @@ int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, long ldx, c
  * transposes, csrc/gemm_wgrad_tma.cu).  Needs 16-byte aligned operands with ldx % 4 == ldy % 4 == 0, m, n >= 32,
  * rows >= 2048; pasnl_gemm_wgrad_tf32x3 routes eligible problems here by itself. */
 int pasnl_gemm_wgrad_tma_eligible(long rows, int m, int n, const void *X, long ldx, const void *Y, long ldy);
+/* x_scale / x_shift (m floats each) or NULL: X is replaced by act(X * x_scale[col] + x_shift[col]) on the way into the
+ * tensor core (x_act 0 none / 1 relu / 2 leaky_relu(0.2)) -- the batch norm + activation of the layer that produced X,
+ * when that layer's normalised output was never materialised (see pasnl_gemm_rows_ws's prologue). */
 int pasnl_gemm_wgrad_tma(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW, long ldw,
-                         int dw_zeroed, void *stream);
+                         int dw_zeroed, const float *x_scale, const float *x_shift, int x_act, void *stream);
 
 
 /* ---------------------------------------------------------------- launch-bound glue of a training step (csrc/small_ops.cu)
@@ -314,6 +317,14 @@ int pasnl_grid_subsample(int n, const float *points, int fdim, const float *feat
  * same swap rule, so ties and the unsorted remainder land where the reference puts them. */
 int pasnl_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out, void *stream);
 int pasnl_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out, void *stream);
+
+/* Batch-norm finalisation without the normalise pass: from the per-column sum / sum of squares of y (ws: 2c doubles, as
+ * accumulated by a GEMM epilogue) -> mean, biased var (saved for the backward), scale = gamma / sqrt(var + eps) and
+ * shift = beta - mean * scale (the operand prologue of the CONSUMING layer's kernels), and the moving-average updates of
+ * pasnl_bn_act_fwd.  Used when act(bn(y)) is folded into the next layer's GEMMs instead of being written out. */
+int pasnl_bn_finalize(long rows, int c, const void *ws, const float *gamma, const float *beta, float eps, const float *bias,
+                      float *running_mean, float *running_var, float decay, int unbiased_moving_var, float *mean,
+                      float *var, float *scale, float *shift, void *stream);
 
 #ifdef __cplusplus
 }

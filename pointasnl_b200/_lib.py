@@ -72,7 +72,8 @@ SIGNATURES = {
     "pasnl_prob_sample": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
     "pasnl_selection_sort": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "pasnl_gemm_wgrad_tma_eligible": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long]),
-    "pasnl_gemm_wgrad_tma": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, c_int, P]),
+    "pasnl_gemm_wgrad_tma": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, c_int, P, P, c_int, P]),
+    "pasnl_bn_finalize": (c_int, [c_long, c_int, P, P, P, c_float, P, P, P, c_float, c_int, P, P, P, P, P]),
     "pasnl_bn_workspace_bytes": (c_size_t, [c_int]),
     "pasnl_bn_act_fwd": (c_int, [c_long, c_int, P, P, P, c_float, c_int, P, P, P, P, P, P, c_float, c_int, c_int, P, P]),
     "pasnl_bn_act_bwd": (c_int, [c_long, c_int, P, P, P, P, P, P, c_float, c_int, P, P, P, c_int, P, P]),

@@ -738,6 +738,101 @@ class DenseBNAct(torch.autograd.Function):
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
 
 
+def _bn_fwd(y, gamma, beta, eps, act, bias, rm, rv, decay, unbiased, stats_ready, ws):
+    rows, cout = y.shape
+    out = torch.empty_like(y)
+    mean = torch.empty((cout,), device=y.device, dtype=torch.float32)
+    var = torch.empty_like(mean)
+    _call("pasnl_bn_act_fwd", rows, cout, _ptr(y), _ptr(gamma), _ptr(beta), float(eps), int(act), _ptr(out), _ptr(mean),
+          _ptr(var), _ptr(bias), _ptr(rm), _ptr(rv), float(decay), 1 if unbiased else 0, 1 if stats_ready else 0, _ptr(ws),
+          _stream())
+    if stats_ready or _bn_single_launch(rows, cout):
+        _lib.launch_count -= 2
+    return out, mean, var
+
+
+def _bn_bwd(y, dout, gamma, beta, mean, var, eps, act):
+    rows, cout = y.shape
+    dy = torch.empty_like(y)
+    dgamma = torch.empty_like(gamma)
+    dbeta = torch.empty_like(beta)
+    ws = _zero_arena.zeros((2 * cout,), torch.float64) if (_zero_arena is not None and _zero_arena.device == y.device) else None
+    ws_zeroed = ws is not None
+    if ws is None:
+        ws = torch.empty((2 * cout,), device=y.device, dtype=torch.float64)
+    _call("pasnl_bn_act_bwd", rows, cout, _ptr(y), _ptr(dout), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), eps, act,
+          _ptr(dy), _ptr(dgamma), _ptr(dbeta), 1 if ws_zeroed else 0, _ptr(ws), _stream())
+    if _bn_single_launch(rows, cout):
+        _lib.launch_count -= 2
+    elif ws_zeroed:
+        _lib.launch_count -= 1
+    return dy, dgamma, dbeta
+
+
+class DenseBNAct2(torch.autograd.Function):
+    """Two stacked 1x1-conv + batch-norm + activation layers (the conv0 -> conv1 pair of a local cell, reference
+    pointasnl_util.py:264-270) whose intermediate activation h1 = act(bn(y1)) is never written: layer 1's statistics come
+    out of its GEMM epilogue, pasnl_bn_finalize turns them into a per-channel scale / shift, and layer 2's GEMM
+    (pasnl_gemm_rows_ws) and weight gradient (pasnl_gemm_wgrad_tma) apply act(y1 * scale + shift) to their operand on
+    the way into the tensor core.  Saves one read + one write of the (rows, c1) tensor per step.  When the shapes do not
+    qualify the function runs the two layers exactly as two DenseBNAct calls would."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2, decay, eps, act1, act2, unbiased):
+        cin, c1 = w1.shape
+        c2 = w2.shape[1]
+        x2 = _rows_view(x, cin)
+        ws1, _ = _zeros((2 * c1,), torch.float64, x2.device)
+        y1, ready1 = gemm_rows(x2, w1, w_kn=True, col_stats=ws1)
+        rows = y1.shape[0]
+        lib = _lib.load()
+        fold = bool(ready1 and _os.environ.get("PASNL_BN_FOLD", "1")[:1] != "0"
+                    and lib.pasnl_gemm_rows_ws_eligible(rows, c1, c2, y1.data_ptr(), c1)
+                    and c2 % 4 == 0 and lib.pasnl_gemm_wgrad_tma_eligible(rows, c1, c2, y1.data_ptr(), c1, y1.data_ptr(), c2))
+        ws2, _ = _zeros((2 * c2,), torch.float64, x2.device)
+        if fold:
+            mean1 = torch.empty((c1,), device=y1.device, dtype=torch.float32)
+            var1, scale1, shift1 = torch.empty_like(mean1), torch.empty_like(mean1), torch.empty_like(mean1)
+            _call("pasnl_bn_finalize", rows, c1, _ptr(ws1), _ptr(g1), _ptr(be1), float(eps), _ptr(b1), _ptr(rm1), _ptr(rv1),
+                  float(decay), 1 if unbiased else 0, _ptr(mean1), _ptr(var1), _ptr(scale1), _ptr(shift1), _stream())
+            y2 = torch.empty((rows, c2), device=y1.device, dtype=torch.float32)
+            _call("pasnl_gemm_rows_ws", rows, c1, c2, _ptr(y1), c1, _ptr(w2), int(w2.stride(0)), 1, _ptr(y2), c2, _ptr(ws2),
+                  _ptr(scale1), _ptr(shift1), int(act1), _stream())
+            ready2, h1 = True, None
+        else:
+            h1, mean1, var1 = _bn_fwd(y1, g1, be1, eps, act1, b1, rm1, rv1, decay, unbiased, ready1, ws1)
+            scale1 = shift1 = None
+            y2, ready2 = gemm_rows(h1, w2, w_kn=True, col_stats=ws2)
+        out, mean2, var2 = _bn_fwd(y2, g2, be2, eps, act2, b2, rm2, rv2, decay, unbiased, ready2, ws2)
+        ctx.save_for_backward(x2, w1, y1, g1, be1, mean1, var1, scale1, shift1, h1, w2, y2, g2, be2, mean2, var2)
+        ctx.meta = (float(eps), int(act1), int(act2), x.shape, fold)
+        return out.reshape(x.shape[:-1] + (c2,))
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w1, y1, g1, be1, mean1, var1, scale1, shift1, h1, w2, y2, g2, be2, mean2, var2 = ctx.saved_tensors
+        eps, act1, act2, xshape, fold = ctx.meta
+        rows, c2 = y2.shape
+        c1 = y1.shape[1]
+        dout = dout.reshape(rows, c2)
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dy2, dg2, dbe2 = _bn_bwd(y2, dout, g2, be2, mean2, var2, eps, act2)
+        dh1 = gemm_rows(dy2, w2, w_kn=False)
+        if fold:
+            dw2, zeroed = _zeros((c1, c2), torch.float32, y1.device)
+            _call("pasnl_gemm_wgrad_tma", rows, c1, c2, _ptr(y1), c1, _ptr(dy2), c2, _ptr(dw2), c2, 1, _ptr(scale1),
+                  _ptr(shift1), act1, _stream())
+        else:
+            dw2 = gemm_wgrad(h1, dy2)
+        dy1, dg1, dbe1 = _bn_bwd(y1, dh1, g1, be1, mean1, var1, eps, act1)
+        dx = gemm_rows(dy1, w1, w_kn=False).reshape(xshape) if ctx.needs_input_grad[0] else None
+        dw1 = gemm_wgrad(x2, dy1)
+        db1 = _zeros(g1.shape, torch.float32, g1.device)[0] if ctx.needs_input_grad[2] else None
+        db2 = _zeros(g2.shape, torch.float32, g2.device)[0] if ctx.needs_input_grad[8] else None
+        return (dx, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None)
+
+
 # ------------------------------------------------------------------ launch-bound glue (csrc/small_ops.cu)
 class AddN(torch.autograd.Function):
     """a + b (+ c): the tf.add chains of the layer functions (pointasnl_util.py:283-285) as one kernel."""

@@ -1420,7 +1420,7 @@ extern "C" int pasnl_gemm_wgrad_tf32x3(long rows, int m, int n, const float *X, 
     if ((m <= 16 || n <= 16) && rows >= 1024) return gtc::launch_wgrad_narrow(rows, m, n, X, ldx, Y, ldy, dW, ldw, zeroed, st);
     // TMA-legal operands: both streamed as MN-major tiles, no transposes (gemm_wgrad_tma.cu)
     if (pasnl_gemm_wgrad_tma_eligible(rows, m, n, X, ldx, Y, ldy))
-        return pasnl_gemm_wgrad_tma(rows, m, n, X, ldx, Y, ldy, dW, ldw, dw_zeroed, stream);
+        return pasnl_gemm_wgrad_tma(rows, m, n, X, ldx, Y, ldy, dW, ldw, dw_zeroed, nullptr, nullptr, 0, stream);
     // long reductions: one warp-specialised CTA per SM with one operand fed through TMEM; short ones keep the
     // several-CTAs-per-SM kernel
     const int ntile = n <= 32 ? 32 : (n <= 64 ? 64 : 128);

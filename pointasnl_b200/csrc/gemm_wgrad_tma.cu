@@ -142,10 +142,12 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap, long rows, long slab,
-                      int m, int n, int nq, float *__restrict__ dW, long ldw) {
+                      int m, int n, int nq, float *__restrict__ dW, long ldw, const float *__restrict__ x_scale,
+                      const float *__restrict__ x_shift, int x_act) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t loaded[kRaw], empty[kRaw], ready[kLo], lofree[kLo], tfull[2], tempty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_scale[128], s_shift[128];   // operand prologue of this CTA's 128 X columns
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     uint8_t *stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *lobuf = stages + (size_t)kRaw * kRawStage;
@@ -155,6 +157,12 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_con
     const int nst = (int)((r_end - r_begin + kKRows - 1) / kKRows);      // stages of 32 rows (TMA zero-fills past `rows`)
     const int nsub = (nst + kSubStages - 1) / kSubStages;
     const int ychunks = nq / 32;
+    const bool pro = x_scale != nullptr;
+    if (pro && t < 128) {
+        const int col = m0 + t;
+        s_scale[t] = col < m ? __ldg(x_scale + col) : 0.f;
+        s_shift[t] = col < m ? __ldg(x_shift + col) : 0.f;
+    }
 
     if (t == 0) {
         for (int s = 0; s < kRaw; ++s) { mbar_init(&loaded[s], 1); mbar_init(&empty[s], 1); }
@@ -232,7 +240,25 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_con
                 float4 *lo = reinterpret_cast<float4 *>(lobuf + (size_t)l * kRawStage + half * kOpBytes) + mt;
                 const int pieces = half == 0 ? 4 : ychunks;            // 256 threads x 16 B = one 4 KB chunk per pass
                 for (int p = 0; p < pieces; ++p) {
-                    const float4 v = hi[256 * p];
+                    float4 v = hi[256 * p];
+                    if (pro && half == 0) {
+                        // X <- act(X * scale[col] + shift[col]) (the producing layer's batch norm + activation).  Thread mt
+                        // holds row mt/8 of the chunk and the 16-byte piece mt%8 of its 128-byte line; the 32-byte atoms
+                        // of a line are XOR-swizzled with (row & 3): logical column = ((piece>>1) ^ (row&3))*8 + (piece&1)*4
+                        const int row = mt >> 3, piece = mt & 7;
+                        const int col = p * 32 + (((piece >> 1) ^ (row & 3)) << 3) + ((piece & 1) << 2);
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + col);
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        if (x_act == 1) {
+                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        } else if (x_act == 2) {
+                            v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+                            v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+                        }
+                        if (r_begin + (long)i * kKRows + row >= r_end) v = make_float4(0.f, 0.f, 0.f, 0.f);   // rows TMA zero-filled
+                    }
                     float4 h, l;
                     h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
                     l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
@@ -333,7 +359,9 @@ extern "C" int pasnl_gemm_wgrad_tma_eligible(long rows, int m, int n, const void
 
 // dW (m, n) += X (rows, m)^T . Y (rows, n); dw_zeroed == 0: the library clears dW first.
 extern "C" int pasnl_gemm_wgrad_tma(long rows, int m, int n, const float *X, long ldx, const float *Y, long ldy, float *dW,
-                                    long ldw, int dw_zeroed, void *stream) {
+                                    long ldw, int dw_zeroed, const float *x_scale, const float *x_shift, int x_act,
+                                    void *stream) {
+    PASNL_CHECK_ARG((x_scale == nullptr) == (x_shift == nullptr) && x_act >= 0 && x_act <= 2);
     PASNL_CHECK_ARG(rows >= 1 && m >= 1 && n >= 1 && ldx >= m && ldy >= n && ldw >= n && X && Y && dW);
     PASNL_CHECK_ARG(pasnl_gemm_wgrad_tma_eligible(rows, m, n, X, ldx, Y, ldy));
     cudaStream_t st = (cudaStream_t)stream;
@@ -355,6 +383,7 @@ extern "C" int pasnl_gemm_wgrad_tma(long rows, int m, int n, const float *X, lon
     const size_t smem = (size_t)(gwt::kRaw + gwt::kLo) * gwt::kRawStage + 1024;
     cudaError_t e = cudaFuncSetAttribute(gwt::gemm_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    gwt::gemm_wgrad_tma_kernel<<<grid, gwt::kThreads, smem, st>>>(xmap, ymap, rows, slab, m, n, nq, dW, ldw);
+    gwt::gemm_wgrad_tma_kernel<<<grid, gwt::kThreads, smem, st>>>(xmap, ymap, rows, slab, m, n, nq, dW, ldw, x_scale, x_shift,
+                                                                  x_act);
     return pasnl_launch_status();
 }

@@ -395,6 +395,26 @@ __global__ void __launch_bounds__(256) col_sum_kernel(long rows, int n, const fl
     }
 }
 
+__global__ void bn_finalize_kernel(long rows, int c, const double *__restrict__ ws, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float eps, const float *__restrict__ bias,
+                                   float *__restrict__ running_mean, float *__restrict__ running_var, float decay,
+                                   float vcorr, float *__restrict__ mean, float *__restrict__ var,
+                                   float *__restrict__ scale, float *__restrict__ shift) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    const double n = (double)rows, m = ws[ch] / n;
+    double vv = ws[c + ch] / n - m * m;
+    if (vv < 0.0) vv = 0.0;
+    const float mf = (float)m, vf = (float)vv;
+    const float sc = rsqrtf(vf + eps) * __ldg(gamma + ch);
+    mean[ch] = mf;
+    var[ch] = vf;
+    scale[ch] = sc;
+    shift[ch] = fmaf(-mf, sc, __ldg(beta + ch));
+    if (running_mean) running_mean[ch] = decay * running_mean[ch] + (1.f - decay) * (mf + (bias ? bias[ch] : 0.f));
+    if (running_var) running_var[ch] = decay * running_var[ch] + (1.f - decay) * vf * vcorr;
+}
+
 }  // namespace sops
 
 extern "C" int pasnl_gemm_skinny(int rows, int ni, int nj, const float *in, long ldin, const float *W, long ldw,
@@ -561,5 +581,16 @@ extern "C" int pasnl_take_cols(long rows, int nc, const float *src, long lds, fl
     if (rows == 0) return PASNL_OK;
     const long tot = rows * nc;
     sops::take_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, nc, src, lds, dst);
+    return pasnl_launch_status();
+}
+
+extern "C" int pasnl_bn_finalize(long rows, int c, const void *ws, const float *gamma, const float *beta, float eps,
+                                 const float *bias, float *running_mean, float *running_var, float decay,
+                                 int unbiased_moving_var, float *mean, float *var, float *scale, float *shift, void *stream) {
+    PASNL_CHECK_ARG(rows >= 1 && c >= 1 && ws && gamma && beta && mean && var && scale && shift);
+    const float vcorr = (unbiased_moving_var && rows > 1) ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+    sops::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rows, c, (const double *)ws, gamma, beta, eps, bias,
+                                                                               running_mean, running_var, decay, vcorr, mean,
+                                                                               var, scale, shift);
     return pasnl_launch_status();
 }

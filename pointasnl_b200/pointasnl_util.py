@@ -361,11 +361,16 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
                                           is_training=is_training, scope="skip", bn_decay=bn_decay,
                                           weight_decay=weight_decay)
         # point local cell (reference :264-280)
-        for i, num_out_channel in enumerate(mlp):
-            if i != len(mlp) - 1:
-                new_point = tf_util.conv2d(new_point, num_out_channel, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
-                                           is_training=is_training, scope="conv%d" % i, bn_decay=bn_decay,
-                                           weight_decay=weight_decay)
+        if len(mlp) == 3 and bn:
+            # conv0 -> conv1 as one fused pair (conv0's activation stays a GEMM-operand prologue of conv1)
+            new_point = tf_util.conv2d_pair(new_point, mlp[:2], ("conv0", "conv1"), bn_decay=bn_decay,
+                                            is_training=is_training, weight_decay=weight_decay)
+        else:
+            for i, num_out_channel in enumerate(mlp):
+                if i != len(mlp) - 1:
+                    new_point = tf_util.conv2d(new_point, num_out_channel, [1, 1], padding="VALID", stride=[1, 1], bn=bn,
+                                               is_training=is_training, scope="conv%d" % i, bn_decay=bn_decay,
+                                               weight_decay=weight_decay)
         weight = weight_net_hidden(grouped_xyz, [32], scope="weight_net", is_training=is_training, bn_decay=bn_decay,
                                    weight_decay=weight_decay)
         new_point = _ops.pointconv_contract(new_point, weight)             # per group (C' x K)(K x 32), one kernel

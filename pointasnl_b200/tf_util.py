@@ -292,6 +292,37 @@ def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="S
     return out
 
 
+def conv2d_pair(inputs, channels, scopes, bn_decay=None, is_training=None, weight_decay=None, activation_fn=relu,
+                use_xavier=True, stddev=1e-3):
+    """Two stacked conv2d([1,1], bn=True) layers -- the same variables, in the same order and scopes, as
+    conv2d(conv2d(inputs, channels[0], scope=scopes[0]), channels[1], scope=scopes[1]) -- run as one fused pair on CUDA in
+    training mode (_ops.DenseBNAct2: the activation between the two layers is never written to memory); otherwise the
+    two conv2d calls themselves."""
+    code = _act_code(activation_fn)
+    if not (inputs.is_cuda and bool(is_training) and code is not None and inputs.dtype == torch.float32):
+        for c, sc in zip(channels, scopes):
+            inputs = conv2d(inputs, c, [1, 1], sc, padding="VALID", bn=True, bn_decay=bn_decay, is_training=is_training,
+                            weight_decay=weight_decay, activation_fn=activation_fn, use_xavier=use_xavier, stddev=stddev)
+        return inputs
+    from . import _ops
+    store = get_default_store()
+    decay = 0.9 if bn_decay is None else float(bn_decay)
+    cin = inputs.shape[-1]
+    args = []
+    for c, sc in zip(channels, scopes):
+        with store.variable_scope(sc):
+            w = _weights((1, 1, cin, c), cin, c, use_xavier, stddev, weight_decay)
+            bias = store.get_variable("biases", (c,), constant_init(0.0))
+            with store.variable_scope("bn"):
+                beta = store.get_variable("beta", (c,), constant_init(0.0))
+                gamma = store.get_variable("gamma", (c,), constant_init(1.0))
+                mean = store.get_variable("moving_mean", (c,), constant_init(0.0), trainable=False)
+                var = store.get_variable("moving_variance", (c,), constant_init(1.0), trainable=False)
+        args += [w.view(cin, c), bias, gamma, beta, mean, var]
+        cin = c
+    return _ops.DenseBNAct2.apply(inputs, *args, decay, 1e-3, code, code, True)
+
+
 def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], padding="SAME", data_format="NHWC",
            use_xavier=True, stddev=1e-3, weight_decay=None, activation_fn=relu, bn=False, bn_decay=None,
            is_training=None):

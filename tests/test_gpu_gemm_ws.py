@@ -102,7 +102,8 @@ def test_wgrad_tma_mn_major_matches_fp64(cuda, rows, m, n):
     dy = torch.randn(rows, n, device=cuda)
     assert _lib.load().pasnl_gemm_wgrad_tma_eligible(rows, m, n, x.data_ptr(), m, dy.data_ptr(), n) == 1
     dw = torch.empty(m, n, device=cuda)
-    _lib.call("pasnl_gemm_wgrad_tma", rows, m, n, x.data_ptr(), m, dy.data_ptr(), n, dw.data_ptr(), n, 0, _ops._stream())
+    _lib.call("pasnl_gemm_wgrad_tma", rows, m, n, x.data_ptr(), m, dy.data_ptr(), n, dw.data_ptr(), n, 0, None, None, 0,
+              _ops._stream())
     want = x.double().t() @ dy.double()
     err = float((dw.double() - want).abs().max()) / float(want.abs().max())
     print(f"   rows={rows} m={m} n={n}: max error {err:.2e} of the largest entry")
@@ -120,3 +121,44 @@ def test_tall_dgrad_with_134_columns_splits_onto_the_ws_kernel(cuda):
     want = dy.double() @ w.double().t()
     assert tuple(dx.shape) == (262144, 134)
     assert float((dx.double() - want).abs().max()) / float(want.abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("rows,cin,c1,c2,act", [(40960, 9, 64, 64, 1), (38000, 134, 128, 128, 2), (40960, 64, 128, 64, 1),
+                                                 (3000, 16, 64, 64, 1)])
+def test_dense_bn_act_pair_matches_two_layers(rows, cin, c1, c2, act):
+    """DenseBNAct2 (conv0's activation folded into conv1's GEMM / weight-gradient operand prologue) against two
+    DenseBNAct calls: outputs, every gradient and the moving statistics.  (3000 rows: the unfused fallback.)"""
+    from pointasnl_b200 import _ops
+    g = torch.Generator(device="cpu").manual_seed(rows + c1)
+    dev = "cuda"
+    x = torch.randn(rows, cin, generator=g).to(dev).requires_grad_(True)
+
+    def params():
+        gg = torch.Generator(device="cpu").manual_seed(5)
+        out = []
+        k = cin
+        for c in (c1, c2):
+            out += [(torch.randn(k, c, generator=gg) / k ** 0.5).to(dev).requires_grad_(True),
+                    torch.zeros(c, device=dev, requires_grad=True),
+                    (1 + 0.3 * torch.randn(c, generator=gg)).to(dev).requires_grad_(True),
+                    (0.3 * torch.randn(c, generator=gg)).to(dev).requires_grad_(True),
+                    torch.zeros(c, device=dev), torch.ones(c, device=dev)]
+            k = c
+        return out
+    dout = torch.randn(rows, c2, generator=g).to(dev)
+    pa, pb = params(), params()
+    h = _ops.DenseBNAct.apply(x, *pa[:6], 0.9, 1e-3, act, True)
+    ref = _ops.DenseBNAct.apply(h, *pa[6:], 0.9, 1e-3, act, True)
+    ref.backward(dout)
+    gx_ref = x.grad.clone()
+    x.grad = None
+    out = _ops.DenseBNAct2.apply(x, *pb, 0.9, 1e-3, act, act, True)
+    out.backward(dout)
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= 2e-5 * scale
+    assert (x.grad - gx_ref).abs().max().item() <= 1e-4 * gx_ref.abs().max().item()
+    for a, b in zip(pa, pb):
+        if a.requires_grad:
+            assert (a.grad - b.grad).abs().max().item() <= 1e-4 * max(a.grad.abs().max().item(), 1e-3)
+        else:
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)

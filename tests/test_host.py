@@ -60,11 +60,10 @@ def test_ops_refuse_cpu_tensors_there_is_no_fallback():
     x = torch.zeros(1, 16, 3)
     for fn in (lambda: tf_sampling.farthest_point_sample(4, x), lambda: tf_grouping.knn_point(2, x, x),
                lambda: tf_grouping.query_ball_point(0.1, 2, x, x), lambda: tf_interpolate.three_nn(x, x),
-               lambda: pointasnl_util.knn_query(2, x, x), lambda: pointasnl_util.sampling(4, x)):
+               lambda: pointasnl_util.knn_query(2, x, x), lambda: pointasnl_util.sampling(4, x),
+               lambda: tf_sampling.prob_sample(x, x)):
         with pytest.raises(ValueError, match="no CPU path"):
             fn()
-    with pytest.raises(NotImplementedError):
-        tf_sampling.prob_sample(x, x)
 
 
 def test_shard_range_partitions_clouds():
