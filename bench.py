@@ -198,23 +198,26 @@ def algorithmic_work(name, a):
     if name == "pasnl_gemm_rows_tf32x3":
         rows, k, n = a[0:3]
         return 4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n, gemm_bound(4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n)
-    if name == "pasnl_gemm_wgrad_tf32x3":
+    if name in ("pasnl_gemm_wgrad_tf32x3", "pasnl_gemm_wgrad_tma"):
         rows, m, n = a[0:3]
         return 4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n, gemm_bound(4 * rows * (m + n) + 4 * m * n, 2 * rows * m * n)
     if name == "pasnl_bn_act_fwd":       # apply reads y and writes out; + one more read of y when the statistics
         rows, c = a[0:2]                 # were not already produced by the GEMM epilogue (stats_ready = argument 15)
         stats_ready = bool(a[15]) if len(a) > 15 and isinstance(a[15], int) else False
         return (8 if stats_ready else 12) * rows * c, 8 * rows * c, "hbm"
+    if name == "pasnl_bn_finalize":      # 2c doubles in, four c-vectors + the moving averages out
+        c = a[1]
+        return 16 * c + 4 * 8 * c, 12 * c, "hbm"
     if name == "pasnl_bn_act_bwd":       # reduce reads y, dout; apply reads y, dout, writes dy
         rows, c = a[0:2]
         return 20 * rows * c, 16 * rows * c, "hbm"
     if name == "pasnl_gemm_rows_ws":
         rows, k, n = a[0:3]
         return 4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n, gemm_bound(4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n)
-    if name == "pasnl_pointconv_fwd":    # x (G,K,C) + w (G,K,32) in, (G,C,32) out
+    if name in ("pasnl_pointconv_fwd", "pasnl_pointconv_fwd_bn"):    # x (G,K,C) + w (G,K,32) in, (G,C,32) out
         g, k, c = a[0:3]
         return 4 * g * (k * c + 32 * k + 32 * c), 2 * g * k * c * 32, "hbm"
-    if name == "pasnl_pointconv_bwd":    # x, w, grad_out in; grad_x, grad_w out
+    if name in ("pasnl_pointconv_bwd", "pasnl_pointconv_bwd_bn"):    # x, w, grad_out in; grad_x, grad_w out
         g, k, c = a[0:3]
         return 4 * g * (2 * k * c + 2 * 32 * k + 32 * c), 4 * g * k * c * 32, "hbm"
     if name in ("pasnl_maxpool_k", "pasnl_maxpool_k_mask"):
@@ -531,7 +534,11 @@ def main():
     # ---- per-kernel pass (eager, CUDA events around each pasnl launch) -> roofline of the dominant kernel
     peaks = load_peaks()
     prof_steps = min(args.steps, 5)
-    ts_prof = ts if args.no_graph else None
+    # the per-launch pass runs with the side / branch streams OFF: every launch is then alone on the device between its
+    # two events (with them on, a launch's events also span the time it shares SMs with the other branch)
+    from pointasnl_b200 import pointasnl_util
+    pointasnl_util.set_concurrency(False)
+    ts_prof = None
     if ts_prof is None:
         ts_prof = TrainStep(wl["model"], batch, points, dev, adaptive_sample=args.AS, use_graph=False, seed=0,
                             overlap_allreduce=False, **wl["kw"])
@@ -548,6 +555,7 @@ def main():
         ts_prof.step()
     ev1.record()
     _lib.profiler = None
+    pointasnl_util.set_concurrency(True)
     rows = prof.table(prof_steps)
     eager_ms = ev0.elapsed_time(ev1) / prof_steps
     ours_ms = sum(r["ms_per_step"] for r in rows)
@@ -555,7 +563,9 @@ def main():
     # (the rows GEMM is one op with two C entry points: pasnl_gemm_rows_tf32x3 routes tall layers to pasnl_gemm_rows_ws and
     #  the Python layer calls the latter directly when it wants the [k][n] weight layout -- they are ranked together)
     def op_of(name):
-        return "pasnl_gemm_rows" if name in ("pasnl_gemm_rows_tf32x3", "pasnl_gemm_rows_ws") else name
+        if name in ("pasnl_gemm_rows_tf32x3", "pasnl_gemm_rows_ws"):
+            return "pasnl_gemm_rows"
+        return "pasnl_gemm_wgrad" if name in ("pasnl_gemm_wgrad_tf32x3", "pasnl_gemm_wgrad_tma") else name
     by_name = {}
     for r in rows:
         by_name[op_of(r["name"])] = by_name.get(op_of(r["name"]), 0.0) + r["ms_per_step"]
@@ -571,7 +581,7 @@ def main():
     roof.update({"traffic": traffic, "kernel": top["name"], "dims": top["dims"],
                  "avg_us": top["avg_us"], "entry_point_ms_per_step": by_name[top_name],
                  "native_bound": top["bound"], "peak_source": peaks["src"],
-                 "timing": f"CUDA events around each launch, eager pass of {prof_steps} steps",
+                 "timing": f"CUDA events around each launch, eager pass of {prof_steps} steps, side/branch streams off",
                  # sum of the event-timed library launches vs the wall time of the same EAGER step (the eager step is
                  # CPU-launch bound, so the ratio understates the share; under ncu the library is 88 % of the device
                  # time of a step: profiles/r01c_launches_cls_step.csv)

@@ -106,6 +106,13 @@ int pasnl_maxpool_k_grad(long groups, int k, int c, const float *x, const float 
 int pasnl_pointconv_fwd(int groups, int k, int c, const float *x, const float *w, float *out, void *stream);
 int pasnl_pointconv_bwd(int groups, int k, int c, const float *x, const float *w, const float *grad_out, float *grad_x,
                         float *grad_w, void *stream);
+/* The same with an operand prologue: x holds the PRE-batch-norm output of the producing layer and is replaced on chip by
+ * act(x * x_scale[ch] + x_shift[ch]) (x_act 0 none / 1 relu / 2 leaky_relu(0.2); c floats each, 16-byte aligned; NULL =
+ * no prologue).  grad_x is the gradient with respect to the TRANSFORMED x (feed it to pasnl_bn_act_bwd). */
+int pasnl_pointconv_fwd_bn(int groups, int k, int c, const float *x, const float *w, float *out, const float *x_scale,
+                           const float *x_shift, int x_act, void *stream);
+int pasnl_pointconv_bwd_bn(int groups, int k, int c, const float *x, const float *w, const float *grad_out, float *grad_x,
+                           float *grad_w, const float *x_scale, const float *x_shift, int x_act, void *stream);
 
 /* ---------------------------------------------------------------- interpolation (tf_ops/3d_interpolation) */
 

@@ -32,6 +32,8 @@ SIGNATURES = {
     "pasnl_group_concat_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P]),
     "pasnl_pointconv_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P]),
     "pasnl_pointconv_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "pasnl_pointconv_fwd_bn": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
+    "pasnl_pointconv_bwd_bn": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, P]),
     "pasnl_maxpool_k": (c_int, [c_long, c_int, c_int, P, P, P]),
     "pasnl_maxpool_k_grad": (c_int, [c_long, c_int, c_int, P, P, P, P, P]),
     "pasnl_three_nn": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),

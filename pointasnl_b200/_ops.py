@@ -272,7 +272,7 @@ class PointConvContract(torch.autograd.Function):
 
 def pointconv_contract(x, w):
     k, c = x.shape[-2], x.shape[-1]
-    if x.is_cuda and w.shape[-1] == 32 and k % 4 == 0 and c % 4 == 0 and k <= 256 and max(2 * (k * c + k * 32), k * c + k * 32 + 2 * c * 32) * 4 <= 200 * 1024:
+    if x.is_cuda and w.shape[-1] == 32 and pointconv_eligible(k, c):
         return PointConvContract.apply(x, w)
     return torch.matmul(x.transpose(-1, -2), w)
 
@@ -769,33 +769,56 @@ def _bn_bwd(y, dout, gamma, beta, mean, var, eps, act):
     return dy, dgamma, dbeta
 
 
+def pair_plan(x2, c1, c2):
+    """Can conv(cin->c1)+BN+act -> conv(c1->c2)+BN+act on the rows of x2 run with the FIRST activation folded into the
+    second layer's kernels?  Needs layer 1's statistics out of its GEMM epilogue, and layer 2's shapes on the
+    weights-stationary TMA GEMM (pasnl_gemm_rows_ws) and the MN-major TMA weight gradient (pasnl_gemm_wgrad_tma).
+    (Fresh torch allocations are >= 256-byte aligned: the intermediate tensors are represented by that alignment.)"""
+    rows, cin = x2.shape
+    if _os.environ.get("PASNL_BN_FOLD", "1")[:1] == "0" or rows <= 64:
+        return False
+    lib = _lib.load()
+    ready1 = bool(lib.pasnl_gemm_rows_ws_eligible(rows, cin, c1, x2.data_ptr(), int(x2.stride(0)))) or cin <= GEMM_K_SLAB
+    return bool(ready1 and lib.pasnl_gemm_rows_ws_eligible(rows, c1, c2, 256, c1) and c2 % 4 == 0
+                and lib.pasnl_gemm_wgrad_tma_eligible(rows, c1, c2, 256, c1, 256, c2))
+
+
 class DenseBNAct2(torch.autograd.Function):
     """Two stacked 1x1-conv + batch-norm + activation layers (the conv0 -> conv1 pair of a local cell, reference
     pointasnl_util.py:264-270) whose intermediate activation h1 = act(bn(y1)) is never written: layer 1's statistics come
     out of its GEMM epilogue, pasnl_bn_finalize turns them into a per-channel scale / shift, and layer 2's GEMM
     (pasnl_gemm_rows_ws) and weight gradient (pasnl_gemm_wgrad_tma) apply act(y1 * scale + shift) to their operand on
     the way into the tensor core.  Saves one read + one write of the (rows, c1) tensor per step.  When the shapes do not
-    qualify the function runs the two layers exactly as two DenseBNAct calls would."""
+    qualify (pair_plan) the function runs the two layers exactly as two DenseBNAct calls would.
+
+    raw_out=True (requires pair_plan): layer 2's normalise + activate pass is left to the consumer as well -- returns
+    (y2, mean2, var2, scale2, shift2) with y2 the PRE-batch-norm output; the consumer (BNActPointConv) applies
+    act(y2 * scale2 + shift2) on chip and returns the gradient with respect to y2, batch-norm terms included."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2, decay, eps, act1, act2, unbiased):
+    def forward(ctx, x, w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2, decay, eps, act1, act2, unbiased,
+                raw_out=False):
         cin, c1 = w1.shape
         c2 = w2.shape[1]
         x2 = _rows_view(x, cin)
+        fold = pair_plan(x2, c1, c2)
+        _require(fold or not raw_out, "DenseBNAct2(raw_out=True) needs shapes that pair_plan() accepts")
         ws1, _ = _zeros((2 * c1,), torch.float64, x2.device)
         y1, ready1 = gemm_rows(x2, w1, w_kn=True, col_stats=ws1)
         rows = y1.shape[0]
-        lib = _lib.load()
-        fold = bool(ready1 and _os.environ.get("PASNL_BN_FOLD", "1")[:1] != "0"
-                    and lib.pasnl_gemm_rows_ws_eligible(rows, c1, c2, y1.data_ptr(), c1)
-                    and c2 % 4 == 0 and lib.pasnl_gemm_wgrad_tma_eligible(rows, c1, c2, y1.data_ptr(), c1, y1.data_ptr(), c2))
+        _require(ready1 or not fold, "internal: pair_plan() and gemm_rows() disagree about fused statistics")
         ws2, _ = _zeros((2 * c2,), torch.float64, x2.device)
+        dev = y1.device
+
+        def finalize(c, ws, g, be, b, rm, rv):
+            mean = torch.empty((c,), device=dev, dtype=torch.float32)
+            var, scale, shift = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
+            _call("pasnl_bn_finalize", rows, c, _ptr(ws), _ptr(g), _ptr(be), float(eps), _ptr(b), _ptr(rm), _ptr(rv),
+                  float(decay), 1 if unbiased else 0, _ptr(mean), _ptr(var), _ptr(scale), _ptr(shift), _stream())
+            return mean, var, scale, shift
         if fold:
-            mean1 = torch.empty((c1,), device=y1.device, dtype=torch.float32)
-            var1, scale1, shift1 = torch.empty_like(mean1), torch.empty_like(mean1), torch.empty_like(mean1)
-            _call("pasnl_bn_finalize", rows, c1, _ptr(ws1), _ptr(g1), _ptr(be1), float(eps), _ptr(b1), _ptr(rm1), _ptr(rv1),
-                  float(decay), 1 if unbiased else 0, _ptr(mean1), _ptr(var1), _ptr(scale1), _ptr(shift1), _stream())
-            y2 = torch.empty((rows, c2), device=y1.device, dtype=torch.float32)
+            mean1, var1, scale1, shift1 = finalize(c1, ws1, g1, be1, b1, rm1, rv1)
+            y2 = torch.empty((rows, c2), device=dev, dtype=torch.float32)
             _call("pasnl_gemm_rows_ws", rows, c1, c2, _ptr(y1), c1, _ptr(w2), int(w2.stride(0)), 1, _ptr(y2), c2, _ptr(ws2),
                   _ptr(scale1), _ptr(shift1), int(act1), _stream())
             ready2, h1 = True, None
@@ -803,24 +826,32 @@ class DenseBNAct2(torch.autograd.Function):
             h1, mean1, var1 = _bn_fwd(y1, g1, be1, eps, act1, b1, rm1, rv1, decay, unbiased, ready1, ws1)
             scale1 = shift1 = None
             y2, ready2 = gemm_rows(h1, w2, w_kn=True, col_stats=ws2)
+        ctx.meta = (float(eps), int(act1), int(act2), x.shape, fold, bool(raw_out))
+        if raw_out:
+            mean2, var2, scale2, shift2 = finalize(c2, ws2, g2, be2, b2, rm2, rv2)
+            ctx.save_for_backward(x2, w1, y1, g1, be1, mean1, var1, scale1, shift1, h1, w2, None, None, None, None, None)
+            ctx.mark_non_differentiable(mean2, var2, scale2, shift2)
+            return y2.reshape(x.shape[:-1] + (c2,)), mean2, var2, scale2, shift2
         out, mean2, var2 = _bn_fwd(y2, g2, be2, eps, act2, b2, rm2, rv2, decay, unbiased, ready2, ws2)
         ctx.save_for_backward(x2, w1, y1, g1, be1, mean1, var1, scale1, shift1, h1, w2, y2, g2, be2, mean2, var2)
-        ctx.meta = (float(eps), int(act1), int(act2), x.shape, fold)
         return out.reshape(x.shape[:-1] + (c2,))
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, *_unused):
         x2, w1, y1, g1, be1, mean1, var1, scale1, shift1, h1, w2, y2, g2, be2, mean2, var2 = ctx.saved_tensors
-        eps, act1, act2, xshape, fold = ctx.meta
-        rows, c2 = y2.shape
-        c1 = y1.shape[1]
+        eps, act1, act2, xshape, fold, raw_out = ctx.meta
+        rows, c1 = y1.shape
+        c2 = w2.shape[1]
         dout = dout.reshape(rows, c2)
         if not dout.is_contiguous():
             dout = dout.contiguous()
-        dy2, dg2, dbe2 = _bn_bwd(y2, dout, g2, be2, mean2, var2, eps, act2)
+        if raw_out:
+            dy2, dg2, dbe2 = dout, None, None          # the consumer already went back through layer 2's batch norm
+        else:
+            dy2, dg2, dbe2 = _bn_bwd(y2, dout, g2, be2, mean2, var2, eps, act2)
         dh1 = gemm_rows(dy2, w2, w_kn=False)
         if fold:
-            dw2, zeroed = _zeros((c1, c2), torch.float32, y1.device)
+            dw2, _zeroed = _zeros((c1, c2), torch.float32, y1.device)
             _call("pasnl_gemm_wgrad_tma", rows, c1, c2, _ptr(y1), c1, _ptr(dy2), c2, _ptr(dw2), c2, 1, _ptr(scale1),
                   _ptr(shift1), act1, _stream())
         else:
@@ -829,8 +860,43 @@ class DenseBNAct2(torch.autograd.Function):
         dx = gemm_rows(dy1, w1, w_kn=False).reshape(xshape) if ctx.needs_input_grad[0] else None
         dw1 = gemm_wgrad(x2, dy1)
         db1 = _zeros(g1.shape, torch.float32, g1.device)[0] if ctx.needs_input_grad[2] else None
-        db2 = _zeros(g2.shape, torch.float32, g2.device)[0] if ctx.needs_input_grad[8] else None
-        return (dx, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None)
+        db2 = _zeros((c2,), torch.float32, g1.device)[0] if ctx.needs_input_grad[8] else None
+        return (dx, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None, None)
+
+
+class BNActPointConv(torch.autograd.Function):
+    """PointConvContract on x = act(batch_norm(y)) with y the PRE-batch-norm output of the producing layer
+    (DenseBNAct2(raw_out=True)): the normalise + activate runs on the tile in shared memory (pasnl_pointconv_*_bn), the
+    backward continues through the batch norm (pasnl_bn_act_bwd) and returns the gradient with respect to y, gamma, beta."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, mean, var, scale, shift, w, eps, act):
+        y, w = _f32(y, "y"), _f32(w, "w")
+        k, c = y.shape[-2], y.shape[-1]
+        _require(w.shape[-1] == 32 and w.shape[:-1] == y.shape[:-1], "weight must be (..., k, 32) matching y (..., k, c)")
+        groups = y.numel() // (k * c)
+        out = torch.empty(y.shape[:-2] + (c, 32), device=y.device, dtype=torch.float32)
+        _call("pasnl_pointconv_fwd_bn", groups, k, c, _ptr(y), _ptr(w), _ptr(out), _ptr(scale), _ptr(shift), int(act),
+              _stream())
+        ctx.save_for_backward(y, w, gamma, beta, mean, var, scale, shift)
+        ctx.meta = (float(eps), int(act))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, w, gamma, beta, mean, var, scale, shift = ctx.saved_tensors
+        eps, act = ctx.meta
+        g = _f32(g, "grad_out")
+        k, c = y.shape[-2], y.shape[-1]
+        gh, gw = torch.empty_like(y), torch.empty_like(w)
+        _call("pasnl_pointconv_bwd_bn", y.numel() // (k * c), k, c, _ptr(y), _ptr(w), _ptr(g), _ptr(gh), _ptr(gw),
+              _ptr(scale), _ptr(shift), act, _stream())
+        dy, dgamma, dbeta = _bn_bwd(y.reshape(-1, c), gh.reshape(-1, c), gamma, beta, mean, var, eps, act)
+        return dy.reshape(y.shape), dgamma, dbeta, None, None, None, None, gw, None, None
+
+
+def pointconv_eligible(k, c):
+    return k % 4 == 0 and c % 4 == 0 and k <= 256 and max(2 * (k * c + k * 32), k * c + k * 32 + 2 * c * 32) * 4 <= 200 * 1024
 
 
 # ------------------------------------------------------------------ launch-bound glue (csrc/small_ops.cu)

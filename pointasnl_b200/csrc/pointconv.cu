@@ -21,6 +21,28 @@ __device__ __forceinline__ void load_tile(float *dst, const float *__restrict__ 
         reinterpret_cast<float4 *>(dst)[v] = __ldg(reinterpret_cast<const float4 *>(src) + v);
 }
 
+// Optional operand prologue (x_scale != NULL): the X tile that arrived in shared memory is the PRE-batch-norm output of the
+// producing layer; it is replaced in place by act(x * scale[ch] + shift[ch]) (act 1 relu / 2 leaky_relu(0.2)) before the
+// contraction, so that layer's normalised activation is never written to HBM (see pasnl_gemm_rows_ws's prologue).
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bn_act_tile(float *X, int nfloats, int c, const float *__restrict__ sc,
+                                            const float *__restrict__ sh, int act) {
+    for (int v = threadIdx.x; v < nfloats / 4; v += blockDim.x) {
+        const int ch = (v * 4) % c;
+        float4 q = reinterpret_cast<float4 *>(X)[v];
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(sc + ch)), b = __ldg(reinterpret_cast<const float4 *>(sh + ch));
+        q.x = fmaf(q.x, a.x, b.x); q.y = fmaf(q.y, a.y, b.y); q.z = fmaf(q.z, a.z, b.z); q.w = fmaf(q.w, a.w, b.w);
+        if (act == 1) {
+            q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f);
+        } else if (act == 2) {
+            q.x = q.x > 0.f ? q.x : 0.2f * q.x; q.y = q.y > 0.f ? q.y : 0.2f * q.y;
+            q.z = q.z > 0.f ? q.z : 0.2f * q.z; q.w = q.w > 0.f ? q.w : 0.2f * q.w;
+        }
+        reinterpret_cast<float4 *>(X)[v] = q;
+    }
+}
+
 // Forward.  Thread tile = 4 channels x 4 weight columns: per neighbour t one LDS.128 of X[t][c..c+3] and one of
 // W[t][w..w+3] feed 16 FMAs.  wg = t & 7 (8 groups of 4 weight columns), cg = t >> 3 (groups of 4 channels): a warp
 // stores 4 full 128-byte rows of the (C x 32) output per instruction.
@@ -29,7 +51,9 @@ __device__ __forceinline__ void load_tile(float *dst, const float *__restrict__ 
 // tiles of the CTA's next group are in flight while the current one is contracted.  (The first version loaded,
 // synchronised, computed, synchronised per group: 43 % of the HBM peak.)
 __global__ void __launch_bounds__(kT) pointconv_fwd_kernel(int groups, int k, int c, const float *__restrict__ x,
-                                                           const float *__restrict__ w, float *__restrict__ out) {
+                                                           const float *__restrict__ w, float *__restrict__ out,
+                                                           const float *__restrict__ x_scale,
+                                                           const float *__restrict__ x_shift, int x_act) {
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t bar[2];
     const int xs = k * c, wsz = k * kWD;
@@ -53,6 +77,11 @@ __global__ void __launch_bounds__(kT) pointconv_fwd_kernel(int groups, int k, in
         // buffer b^1 was last read in iteration it-1, which ended with a CTA barrier
         if (threadIdx.x == 0 && gn < groups) issue(gn, b ^ 1);
         mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+        if (x_scale != nullptr) {
+            bn_act_tile(Xb[b], xs, c, x_scale, x_shift, x_act);
+            fence_async_smem();                 // the tile is rewritten by a later bulk copy (async proxy)
+            __syncthreads();
+        }
         const float *X = Xb[b], *W = Wb[b];
         float *o = out + (size_t)g * c * kWD;
         for (int cg = cg0; cg < c / 4; cg += blockDim.x / 8) {
@@ -88,7 +117,9 @@ template <int NBUF>
 __global__ void __launch_bounds__(kT) pointconv_bwd_kernel(int groups, int k, int c, const float *__restrict__ x,
                                                            const float *__restrict__ w,
                                                            const float *__restrict__ grad_out,
-                                                           float *__restrict__ grad_x, float *__restrict__ grad_w) {
+                                                           float *__restrict__ grad_x, float *__restrict__ grad_w,
+                                                           const float *__restrict__ x_scale,
+                                                           const float *__restrict__ x_shift, int x_act) {
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t bar[2];
     const int xs = k * c, wsz = k * kWD, ms = c * kWD, in_sz = xs + wsz + ms;
@@ -113,6 +144,10 @@ __global__ void __launch_bounds__(kT) pointconv_bwd_kernel(int groups, int k, in
         if (NBUF == 2 && threadIdx.x == 0 && gn < groups) issue(gn, b ^ 1);
         mbar_wait(&bar[b], (uint32_t)(NBUF == 2 ? ((it >> 1) & 1) : (it & 1)));
         const float *X = smem + b * in_sz, *W = X + xs, *dM = W + wsz;
+        if (x_scale != nullptr) {
+            bn_act_tile(smem + b * in_sz, xs, c, x_scale, x_shift, x_act);
+            fence_async_smem();
+        }
         for (int v = threadIdx.x; v < ms / 4; v += blockDim.x) {
             const float4 d = reinterpret_cast<const float4 *>(dM)[v];
             const int ch = v >> 3, w0 = (v & 7) * 4;           // element (ch, w0..w0+3)
@@ -192,7 +227,10 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 }  // namespace
 
-extern "C" int pasnl_pointconv_fwd(int groups, int k, int c, const float *x, const float *w, float *out, void *stream) {
+extern "C" int pasnl_pointconv_fwd_bn(int groups, int k, int c, const float *x, const float *w, float *out,
+                                      const float *x_scale, const float *x_shift, int x_act, void *stream) {
+    PASNL_CHECK_ARG((x_scale == nullptr) == (x_shift == nullptr) && x_act >= 0 && x_act <= 2 && aligned16(x_scale) &&
+                    aligned16(x_shift));
     PASNL_CHECK_ARG(groups >= 0 && k >= 4 && k % 4 == 0 && k <= 256 && c >= 4 && c % 4 == 0 && c <= 1024);
     if (groups == 0) return PASNL_OK;
     PASNL_CHECK_ARG(x && w && out && aligned16(x) && aligned16(w));
@@ -204,12 +242,19 @@ extern "C" int pasnl_pointconv_fwd(int groups, int k, int c, const float *x, con
     int threads = 8 * (c / 4);
     threads = threads > kT ? kT : (threads + 31) / 32 * 32;
     const int grid = groups < 148 * 8 ? groups : 148 * 8;
-    pointconv_fwd_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(groups, k, c, x, w, out);
+    pointconv_fwd_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(groups, k, c, x, w, out, x_scale, x_shift, x_act);
     return pasnl_launch_status();
 }
 
-extern "C" int pasnl_pointconv_bwd(int groups, int k, int c, const float *x, const float *w, const float *grad_out,
-                                   float *grad_x, float *grad_w, void *stream) {
+extern "C" int pasnl_pointconv_fwd(int groups, int k, int c, const float *x, const float *w, float *out, void *stream) {
+    return pasnl_pointconv_fwd_bn(groups, k, c, x, w, out, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int pasnl_pointconv_bwd_bn(int groups, int k, int c, const float *x, const float *w, const float *grad_out,
+                                      float *grad_x, float *grad_w, const float *x_scale, const float *x_shift, int x_act,
+                                      void *stream) {
+    PASNL_CHECK_ARG((x_scale == nullptr) == (x_shift == nullptr) && x_act >= 0 && x_act <= 2 && aligned16(x_scale) &&
+                    aligned16(x_shift));
     PASNL_CHECK_ARG(groups >= 0 && k >= 4 && k % 4 == 0 && k <= 256 && c >= 4 && c % 4 == 0 && c <= 1024);
     if (groups == 0) return PASNL_OK;
     PASNL_CHECK_ARG(x && w && grad_out && grad_x && grad_w && aligned16(x) && aligned16(w) && aligned16(grad_out));
@@ -223,11 +268,18 @@ extern "C" int pasnl_pointconv_bwd(int groups, int k, int c, const float *x, con
     if (dbl) {
         e = cudaFuncSetAttribute(pointconv_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        pointconv_bwd_kernel<2><<<grid, kT, smem, (cudaStream_t)stream>>>(groups, k, c, x, w, grad_out, grad_x, grad_w);
+        pointconv_bwd_kernel<2><<<grid, kT, smem, (cudaStream_t)stream>>>(groups, k, c, x, w, grad_out, grad_x, grad_w, x_scale, x_shift,
+                                                                         x_act);
     } else {
         e = cudaFuncSetAttribute(pointconv_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        pointconv_bwd_kernel<1><<<grid, kT, smem, (cudaStream_t)stream>>>(groups, k, c, x, w, grad_out, grad_x, grad_w);
+        pointconv_bwd_kernel<1><<<grid, kT, smem, (cudaStream_t)stream>>>(groups, k, c, x, w, grad_out, grad_x, grad_w, x_scale, x_shift,
+                                                                         x_act);
     }
     return pasnl_launch_status();
+}
+
+extern "C" int pasnl_pointconv_bwd(int groups, int k, int c, const float *x, const float *w, const float *grad_out,
+                                   float *grad_x, float *grad_w, void *stream) {
+    return pasnl_pointconv_bwd_bn(groups, k, c, x, w, grad_out, grad_x, grad_w, nullptr, nullptr, 0, stream);
 }

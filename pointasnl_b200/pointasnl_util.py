@@ -104,13 +104,25 @@ class branch:
                     t.record_stream(self.main)
 
 
+_prefetch_enabled = True
+
+
+def set_concurrency(enabled):
+    """Switch the side-stream prefetch and the branch streams on / off for the layers built from now on (default on;
+    off = every kernel of a step on the caller's stream, e.g. to time launches one at a time)."""
+    global _prefetch_enabled
+    _prefetch_enabled = bool(enabled)
+    import os
+    branch.enabled = bool(enabled) and os.environ.get("PASNL_BRANCH_STREAMS", "1")[:1] != "0"
+
+
 def prefetch_neighbourhood(xyz, npoint, nsample):
     """Launch the FPS (xyz -> npoint samples) and the k-NN (nsample neighbours of the samples in xyz) of a LATER
     set-abstraction layer NOW, on a side stream: both depend on coordinates only, FPS is a latency chain that occupies
     one CTA (or one cluster) per cloud, and the layers in between keep the other SMs busy (SemanticKITTI shape: 13.9 ms
     of FPS on 16 of 148 SMs next to ~10 ms of layer-0 work).  The results land in the open index_cache(); the layer
     that asks for them joins the side stream.  No-op outside an index_cache() scope or on CPU tensors."""
-    if _memo is None or not xyz.is_cuda:
+    if _memo is None or not xyz.is_cuda or not _prefetch_enabled:
         return
     dev = xyz.device
     main = torch.cuda.current_stream(dev)
@@ -363,6 +375,8 @@ def PointASNLSetAbstraction(xyz, feature, npoint, nsample, mlp, is_training, bn_
         # point local cell (reference :264-280)
         if len(mlp) == 3 and bn:
             # conv0 -> conv1 as one fused pair (conv0's activation stays a GEMM-operand prologue of conv1)
+            # (folding conv1's as well, into the PointConv kernels -- _ops.BNActPointConv -- was measured and is NOT
+            #  used: those kernels are shared-memory bound and lose more than the saved normalise pass)
             new_point = tf_util.conv2d_pair(new_point, mlp[:2], ("conv0", "conv1"), bn_decay=bn_decay,
                                             is_training=is_training, weight_decay=weight_decay)
         else:

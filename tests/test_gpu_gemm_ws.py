@@ -162,3 +162,45 @@ def test_dense_bn_act_pair_matches_two_layers(rows, cin, c1, c2, act):
             assert (a.grad - b.grad).abs().max().item() <= 1e-4 * max(a.grad.abs().max().item(), 1e-3)
         else:
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("b,s,k,cin,c1,c2", [(8, 160, 32, 9, 64, 64), (4, 320, 32, 134, 128, 128)])
+def test_pre_norm_pointconv_matches_materialised(b, s, k, cin, c1, c2):
+    """DenseBNAct2(raw_out=True) + BNActPointConv (conv1's batch norm + ReLU applied to the tile inside the PointConv
+    kernels, backward continued through the batch norm) against DenseBNAct2 + PointConvContract."""
+    from pointasnl_b200 import _ops
+    g = torch.Generator(device="cpu").manual_seed(b + s)
+    dev = "cuda"
+    x = torch.randn(b, s, k, cin, generator=g).to(dev).requires_grad_(True)
+    wn = torch.randn(b, s, k, 32, generator=g).to(dev).requires_grad_(True)
+    assert _ops.pair_plan(x.reshape(-1, cin), c1, c2) and _ops.pointconv_eligible(k, c2)
+
+    def params():
+        gg = torch.Generator(device="cpu").manual_seed(5)
+        out, kk = [], cin
+        for c in (c1, c2):
+            out += [(torch.randn(kk, c, generator=gg) / kk ** 0.5).to(dev).requires_grad_(True),
+                    torch.zeros(c, device=dev, requires_grad=True),
+                    (1 + 0.3 * torch.randn(c, generator=gg)).to(dev).requires_grad_(True),
+                    (0.3 * torch.randn(c, generator=gg)).to(dev).requires_grad_(True),
+                    torch.zeros(c, device=dev), torch.ones(c, device=dev)]
+            kk = c
+        return out
+    dout = torch.randn(b, s, c2, 32, generator=g).to(dev)
+    pa, pb = params(), params()
+    h = _ops.DenseBNAct2.apply(x, *pa, 0.9, 1e-3, 1, 1, True)
+    ref = _ops.PointConvContract.apply(h, wn)
+    ref.backward(dout)
+    gx_ref, gw_ref = x.grad.clone(), wn.grad.clone()
+    x.grad = wn.grad = None
+    y, mean2, var2, scale2, shift2 = _ops.DenseBNAct2.apply(x, *pb, 0.9, 1e-3, 1, 1, True, True)
+    out = _ops.BNActPointConv.apply(y, pb[8], pb[9], mean2, var2, scale2, shift2, wn, 1e-3, 1)
+    out.backward(dout)
+    assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert (x.grad - gx_ref).abs().max().item() <= 1e-4 * gx_ref.abs().max().item()
+    assert (wn.grad - gw_ref).abs().max().item() <= 1e-4 * gw_ref.abs().max().item()
+    for a, c in zip(pa, pb):
+        if a.requires_grad:
+            assert (a.grad - c.grad).abs().max().item() <= 1e-4 * max(a.grad.abs().max().item(), 1e-3)
+        else:
+            assert torch.allclose(a, c, rtol=1e-5, atol=1e-6)
