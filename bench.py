@@ -303,12 +303,16 @@ class KernelProfiler:
                 dims.append(round(v, 6) if isinstance(v, float) else int(v))
             key = (name,) + tuple(dims)
             r = agg.setdefault(key, {"name": name, "dims": list(key[1:]), "calls": 0, "ms": 0.0, "bytes": by,
-                                     "flops": fl, "bound": bound})
+                                     "flops": fl, "bound": bound, "_all": []})
             r["calls"] += 1
-            r["ms"] += ms
+            r["_all"].append(ms)
         rows = []
         for r in agg.values():
-            avg = r["ms"] / r["calls"]
+            # MEDIAN launch duration x calls: the eager pass is CPU-bound, so an event pair occasionally also spans a host
+            # hiccup (allocator, GC) between the start event and the launch -- one such outlier must not pick the kernel
+            samples = sorted(r.pop("_all"))
+            avg = samples[len(samples) // 2]
+            r["ms"] = avg * r["calls"]
             rows.append({**r, "avg_us": 1e3 * avg, "ms_per_step": r["ms"] / steps,
                          "roof_ms_per_step": 1e3 * roof_seconds(r["bytes"], r["flops"], r["bound"], load_peaks()) * r["calls"] / steps,
                          "gbs": r["bytes"] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0,
@@ -581,7 +585,7 @@ def main():
     roof.update({"traffic": traffic, "kernel": top["name"], "dims": top["dims"],
                  "avg_us": top["avg_us"], "entry_point_ms_per_step": by_name[top_name],
                  "native_bound": top["bound"], "peak_source": peaks["src"],
-                 "timing": f"CUDA events around each launch, eager pass of {prof_steps} steps, side/branch streams off",
+                 "timing": f"CUDA events around each launch (median per shape), eager pass of {prof_steps} steps, side/branch streams off",
                  # sum of the event-timed library launches vs the wall time of the same EAGER step (the eager step is
                  # CPU-launch bound, so the ratio understates the share; under ncu the library is 88 % of the device
                  # time of a step: profiles/r01c_launches_cls_step.csv)

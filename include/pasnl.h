@@ -210,6 +210,8 @@ int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, co
  * (pro_act 0 none / 1 relu / 2 leaky_relu(0.2)): the batch-norm normalise + activation of the producing layer, applied
  * on the way into the tensor core instead of in a pass of its own (utils/tf_util.py:170-185). */
 int pasnl_gemm_rows_ws_eligible(long rows, int k, int n, const void *A, long lda);
+/* n > 128 with k <= 128 (products bound by writing C): one 128-column weight block per CTA; same entry point. */
+int pasnl_gemm_rows_ws_wide_eligible(long rows, int k, int n, const void *A, long lda);
 int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long lda, const float *W, long ldw, int w_kn, float *C,
                        long ldc, double *col_stats, const float *pro_scale, const float *pro_shift, int pro_act,
                        void *stream);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pasnl_nl_core_bwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, P, P, P, P, P]),
     "pasnl_gemm_rows_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),
     "pasnl_gemm_rows_ws_eligible": (c_int, [c_long, c_int, c_int, P, c_long]),
+    "pasnl_gemm_rows_ws_wide_eligible": (c_int, [c_long, c_int, c_int, P, c_long]),
     "pasnl_gemm_rows_ws": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, c_int, P, c_long, P, P, P, c_int, P]),
     "pasnl_gemm_rows_tma_eligible": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long]),
     "pasnl_gemm_rows_tma": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),

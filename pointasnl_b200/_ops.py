@@ -618,8 +618,9 @@ def transposed_weight(w2d):
 def gemm_rows(a, w, w_kn=False, col_stats=None):
     """a (rows, k) times a weight -> (rows, n), fp32-accurate (3xTF32 on tcgen05, fp32 FMA for rows <= 64).
     w is [n][k] (w_kn=False: the transposed form, e.g. the stored weight seen from the input-gradient product) or [k][n]
-    (w_kn=True: the layer's stored weight).  Routing: rows <= 64 -> pasnl_gemm_skinny; tall layers with k, n <= 128 ->
-    pasnl_gemm_rows_ws (TMA-fed, weights stationary in TMEM; takes either layout); everything else ->
+    (w_kn=True: the layer's stored weight).  Routing: rows <= 64 -> pasnl_gemm_skinny; tall layers with k, n <= 128, and
+    k <= 128 with many output columns (bound by writing C) -> pasnl_gemm_rows_ws (TMA-fed, weights stationary in TMEM;
+    takes either layout); everything else ->
     pasnl_gemm_rows_tf32x3, which wants [n][k] (a [k][n] weight goes through the step's batched transpose).
     col_stats: optional zeroed (2n,) float64 tensor; when the kernel's epilogue can accumulate the per-column sum / sum
     of squares of the result into it the function returns (c, True), else (c, False)."""
@@ -635,7 +636,8 @@ def gemm_rows(a, w, w_kn=False, col_stats=None):
               _ptr(c), n, _stream())
         return c if col_stats is None else (c, False)
     lib = _lib.load()
-    if lib.pasnl_gemm_rows_ws_eligible(rows, k, n, a.data_ptr(), int(a.stride(0))):
+    if (lib.pasnl_gemm_rows_ws_eligible(rows, k, n, a.data_ptr(), int(a.stride(0)))
+            or lib.pasnl_gemm_rows_ws_wide_eligible(rows, k, n, a.data_ptr(), int(a.stride(0)))):
         c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
         _call("pasnl_gemm_rows_ws", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(w), int(w.stride(0)), 1 if w_kn else 0,
               _ptr(c), n, _ptr(col_stats), None, None, 0, _stream())

@@ -1370,7 +1370,7 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
     PASNL_CHECK_ARG(A && Bt && C && rows / 128 < 2147483647L && n <= 256 * 65535);
     cudaStream_t st = (cudaStream_t)stream;
     // tall layers whose weights fit one TMEM-resident tile: TMA-fed, weights-stationary kernel (gemm_ws.cu)
-    if (pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda))
+    if (pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda) || pasnl_gemm_rows_ws_wide_eligible(rows, k, n, A, lda))
         return pasnl_gemm_rows_ws(rows, k, n, A, lda, Bt, ldb, 0, C, ldc, col_stats, nullptr, nullptr, 0, stream);
     // mid-size layers with TMA-legal operands: both operands by TMA, any k (gemm_tma.cu)
     if (pasnl_gemm_rows_tma_eligible(rows, k, n, A, lda, Bt, ldb))

@@ -147,6 +147,8 @@ gemm_rows_ws_kernel(const __grid_constant__ CUtensorMap amap, long rows, int k, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    // blockIdx.y = 128-column block of the output (n > 128: the "wide" launch, one weight block per CTA)
+    const int n0 = blockIdx.y * 128, n_here = min(128, n - n0);
     if (warp < 4) {   // W^T -> TMEM, split once: lane = output channel, column = k
         const int ch = warp * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
@@ -156,7 +158,7 @@ gemm_rows_ws_kernel(const __grid_constant__ CUtensorMap amap, long rows, int k, 
             for (int i = 0; i < 8; ++i) {
                 const int kk = k0 + i;
                 float w = 0.f;
-                if (ch < n && kk < k) w = w_kn ? __ldg(W + (long)kk * ldw + ch) : __ldg(W + (long)ch * ldw + kk);
+                if (ch < n_here && kk < k) w = w_kn ? __ldg(W + (long)kk * ldw + n0 + ch) : __ldg(W + (long)(n0 + ch) * ldw + kk);
                 hi[i] = tf32_hi(w);
                 lo[i] = w - hi[i];
             }
@@ -270,7 +272,7 @@ gemm_rows_ws_kernel(const __grid_constant__ CUtensorMap amap, long rows, int k, 
     } else {
         // ------------------------------------------------------------------ epilogue: C^T rows = this thread's channel
         const int ch = warp * 32 + lane;
-        const bool chv = ch < n;
+        const bool chv = ch < n_here;
         const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
         double S1 = 0.0, S2 = 0.0;
         long cnt = 0;
@@ -293,7 +295,7 @@ gemm_rows_ws_kernel(const __grid_constant__ CUtensorMap amap, long rows, int k, 
                     if (lane == 0) mbar_arrive(&tempty[b]);
                 }
                 if (!have_shift) { shiftv = v[0]; have_shift = true; }
-                float *dst = C + (row0 + q * 32) * ldc + ch;
+                float *dst = C + (row0 + q * 32) * ldc + n0 + ch;
                 if (chv) {
                     if (q * 32 + 32 <= nv) {
 #pragma unroll
@@ -322,8 +324,8 @@ gemm_rows_ws_kernel(const __grid_constant__ CUtensorMap amap, long rows, int k, 
         }
         if (stats != nullptr && chv && cnt > 0) {
             const double kd = (double)shiftv, c = (double)cnt;
-            atomicAdd(stats + ch, S1 + c * kd);
-            atomicAdd(stats + n + ch, S2 + 2.0 * kd * S1 + c * kd * kd);
+            atomicAdd(stats + n0 + ch, S1 + c * kd);
+            atomicAdd(stats + n + n0 + ch, S2 + 2.0 * kd * S1 + c * kd * kd);
         }
     }
     tc_fence_before();
@@ -379,6 +381,25 @@ extern "C" int pasnl_gemm_rows_ws_eligible(long rows, int k, int n, const void *
     return 1;
 }
 
+// n > 128 ("wide"): the same kernel with one 128-column weight block per CTA (blockIdx.y) and the row tiles of a block shared
+// by sm_count / blocks persistent CTAs; A (k <= 128 columns) is re-read per block out of L2.  For products that are bound
+// by WRITING C (the input gradient of the [1,K] after_conv layer: 16384 x 128 -> 2048, 134 MB out) the coalesced
+// C^T-epilogue stores are what matters.  Eligible when there are enough (row tile, block) pairs to amortise the per-CTA
+// weight split: >= 4 per SM.
+extern "C" int pasnl_gemm_rows_ws_wide_eligible(long rows, int k, int n, const void *A, long lda) {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("PASNL_GEMM_WS_WIDE");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (!on || gws::encode_fn() == nullptr) return 0;
+    if (k <= 32 || k > 128 || n <= 128 || n > 128 * 64) return 0;
+    if ((lda % 4) != 0 || (reinterpret_cast<uintptr_t>(A) & 15u) != 0) return 0;
+    const long ntiles = (rows + gws::kRows - 1) / gws::kRows, nblocks = (n + 127) / 128;
+    if (nblocks > gws::sm_count() || ntiles * nblocks < 4L * gws::sm_count() || ntiles >= 2147483647L / gws::kRows) return 0;
+    return 1;
+}
+
 // C[rows, n] = f(A)[rows, k] . W.  W is [k][n] (w_kn != 0, pitch ldw) or [n][k] (w_kn == 0).  col_stats (2n doubles,
 // zero-initialised by the caller) or NULL: += per-column sum and sum of squares of C.  pro_scale / pro_shift (k floats
 // each) or NULL: f(a) = act(a * scale[col] + shift[col]), pro_act 0 none / 1 relu / 2 leaky_relu(0.2).
@@ -387,7 +408,8 @@ extern "C" int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long 
                                   int pro_act, void *stream) {
     PASNL_CHECK_ARG(rows >= 0 && k >= 1 && n >= 1 && lda >= k && ldc >= n && (w_kn ? ldw >= n : ldw >= k));
     if (rows == 0) return PASNL_OK;
-    PASNL_CHECK_ARG(A && W && C && pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda));
+    PASNL_CHECK_ARG(A && W && C && (pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda) ||
+                                    pasnl_gemm_rows_ws_wide_eligible(rows, k, n, A, lda)));
     PASNL_CHECK_ARG((pro_scale == nullptr) == (pro_shift == nullptr) && pro_act >= 0 && pro_act <= 2);
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap map;
@@ -401,7 +423,11 @@ extern "C" int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long 
     if (r != CUDA_SUCCESS) return PASNL_EINVAL;
     const int kpad = (k + gws::kKB - 1) / gws::kKB * gws::kKB;
     const long ntiles = (rows + gws::kRows - 1) / gws::kRows;
-    const int grid = (int)(ntiles < gws::sm_count() ? ntiles : gws::sm_count());
+    const int nblocks = (n + 127) / 128;
+    long gx = gws::sm_count() / nblocks;                       // persistent CTAs per column block
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    const dim3 grid((unsigned)gx, (unsigned)nblocks);
     const size_t smem = (size_t)gws::kStages * gws::kStageBytes + 1024;
     cudaError_t e = cudaFuncSetAttribute(gws::gemm_rows_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

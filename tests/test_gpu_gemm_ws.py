@@ -15,7 +15,9 @@ def run_ws(a, w, w_kn, stats=False, pro=None, act=0, ldc=None):
     c = torch.full((rows, ldc), 7.0, device=a.device)
     st = torch.zeros(2 * n, dtype=torch.float64, device=a.device) if stats else None
     sc, sh = (pro if pro is not None else (None, None))
-    assert _lib.load().pasnl_gemm_rows_ws_eligible(rows, k, n, a.data_ptr(), a.stride(0)) == 1
+    lib = _lib.load()
+    assert (lib.pasnl_gemm_rows_ws_eligible(rows, k, n, a.data_ptr(), a.stride(0)) == 1
+            or lib.pasnl_gemm_rows_ws_wide_eligible(rows, k, n, a.data_ptr(), a.stride(0)) == 1)
     _lib.call("pasnl_gemm_rows_ws", rows, k, n, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), 1 if w_kn else 0,
               c.data_ptr(), ldc, _ops._ptr(st), _ops._ptr(sc), _ops._ptr(sh), act, _ops._stream())
     return c, st
@@ -40,6 +42,28 @@ def test_rows_ws_matches_fp64(cuda, rows, k, n, w_kn):
     # (fp32 partial sums per 128-row tile, fp64 across tiles: ~1e-7 of sum |x|)
     torch.testing.assert_close(st[:n], cd.sum(0), rtol=1e-7, atol=2e-7 * scale * rows)
     torch.testing.assert_close(st[n:], (cd * cd).sum(0), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("rows,k,n", [(16384, 128, 2048), (4100, 64, 2500), (9000, 100, 1028)])
+@pytest.mark.parametrize("w_kn", [False, True])
+def test_rows_ws_wide_column_blocks_match_fp64(cuda, rows, k, n, w_kn):
+    """n > 128: one 128-column weight block per CTA (blockIdx.y), ragged last block and row tile, fused statistics."""
+    torch.manual_seed(rows + n)
+    a = torch.randn(rows, k, device=cuda) * 1.1 - 0.1
+    w = torch.randn(k, n, device=cuda) / k ** 0.5
+    wt = w if w_kn else w.t().contiguous()
+    c, st = run_ws(a, wt, w_kn, stats=True, ldc=n + 4)
+    want = a.double() @ w.double()
+    scale = float(want.abs().max())
+    assert float((c[:, :n].double() - want).abs().max()) / scale < 5e-6
+    assert bool((c[:, n:] == 7.0).all())
+    cd = c[:, :n].double()
+    torch.testing.assert_close(st[:n], cd.sum(0), rtol=1e-7, atol=2e-7 * scale * rows)
+    torch.testing.assert_close(st[n:], (cd * cd).sum(0), rtol=1e-6, atol=1e-9)
+    # and the router sends the shape here
+    from pointasnl_b200 import _ops
+    got = _ops.gemm_rows(a, wt, w_kn=w_kn)
+    assert torch.equal(got, c[:, :n].contiguous())
 
 
 @pytest.mark.parametrize("act", [0, 1, 2])
