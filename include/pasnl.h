@@ -212,11 +212,6 @@ int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, long lda, co
 int pasnl_gemm_rows_ws_eligible(long rows, int k, int n, const void *A, long lda);
 /* n > 128 with k <= 128 (products bound by writing C): one 128-column weight block per CTA; same entry point. */
 int pasnl_gemm_rows_ws_wide_eligible(long rows, int k, int n, const void *A, long lda);
-/* 128 < k <= 256 with many output columns: two <= 128-wide k slabs through the wide launch, the second adding into C
- * (no statistics, no prologue). */
-int pasnl_gemm_rows_ws_kslabs_eligible(long rows, int k, int n, const void *A, long lda);
-int pasnl_gemm_rows_ws_kslabs(long rows, int k, int n, const float *A, long lda, const float *W, long ldw, int w_kn,
-                              float *C, long ldc, void *stream);
 int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long lda, const float *W, long ldw, int w_kn, float *C,
                        long ldc, double *col_stats, const float *pro_scale, const float *pro_shift, int pro_act,
                        void *stream);

@@ -49,8 +49,6 @@ SIGNATURES = {
     "pasnl_gemm_rows_tf32x3": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),
     "pasnl_gemm_rows_ws_eligible": (c_int, [c_long, c_int, c_int, P, c_long]),
     "pasnl_gemm_rows_ws_wide_eligible": (c_int, [c_long, c_int, c_int, P, c_long]),
-    "pasnl_gemm_rows_ws_kslabs_eligible": (c_int, [c_long, c_int, c_int, P, c_long]),
-    "pasnl_gemm_rows_ws_kslabs": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, c_int, P, c_long, P]),
     "pasnl_gemm_rows_ws": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, c_int, P, c_long, P, P, P, c_int, P]),
     "pasnl_gemm_rows_tma_eligible": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long]),
     "pasnl_gemm_rows_tma": (c_int, [c_long, c_int, c_int, P, c_long, P, c_long, P, c_long, P, P]),
@@ -102,7 +100,7 @@ KERNELS_PER_CALL = {
     "pasnl_gather_point_grad": 2, "pasnl_gather_rows_grad": 2, "pasnl_group_point_grad": 2,
     "pasnl_three_interpolate_grad": 2, "pasnl_group_concat_grad": 4, "pasnl_nl_core_bwd": 3,
     "pasnl_bn_act_fwd": 3, "pasnl_bn_act_bwd": 3, "pasnl_gemm_wgrad_tf32x3": 2, "pasnl_softmax_ce_fwd": 2,
-    "pasnl_adam_l2": 2, "pasnl_gemm_rows_ws_kslabs": 2, "pasnl_col_sum": 2, "pasnl_grid_subsample": 15, "pasnl_prob_sample": 2,
+    "pasnl_adam_l2": 2, "pasnl_col_sum": 2, "pasnl_grid_subsample": 15, "pasnl_prob_sample": 2,
 }
 
 

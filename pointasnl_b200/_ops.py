@@ -642,13 +642,6 @@ def gemm_rows(a, w, w_kn=False, col_stats=None):
         _call("pasnl_gemm_rows_ws", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(w), int(w.stride(0)), 1 if w_kn else 0,
               _ptr(c), n, _ptr(col_stats), None, None, 0, _stream())
         return c if col_stats is None else (c, True)
-    if (col_stats is None and _os.environ.get("PASNL_GEMM_WS_KSLABS", "0")[:1] == "1"       # opt-in: measured slower
-            and lib.pasnl_gemm_rows_ws_kslabs_eligible(rows, k, n, a.data_ptr(), int(a.stride(0)))):
-        # 128 < k <= 256 onto many output columns (bound by writing C): two k slabs through the wide launch
-        c = torch.empty((rows, n), device=a.device, dtype=torch.float32)
-        _call("pasnl_gemm_rows_ws_kslabs", rows, k, n, _ptr(a), int(a.stride(0)), _ptr(w), int(w.stride(0)),
-              1 if w_kn else 0, _ptr(c), n, _stream())
-        return c
     if (col_stats is None and not w_kn and 128 < n <= 160
             and lib.pasnl_gemm_rows_ws_eligible(rows, k, 128, a.data_ptr(), int(a.stride(0)))):
         # a tall input-gradient product with a few more than 128 output columns (the 134-wide grouped tensor of cls

@@ -1372,13 +1372,6 @@ extern "C" int pasnl_gemm_rows_tf32x3(long rows, int k, int n, const float *A, l
     // tall layers whose weights fit one TMEM-resident tile: TMA-fed, weights-stationary kernel (gemm_ws.cu)
     if (pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda) || pasnl_gemm_rows_ws_wide_eligible(rows, k, n, A, lda))
         return pasnl_gemm_rows_ws(rows, k, n, A, lda, Bt, ldb, 0, C, ldc, col_stats, nullptr, nullptr, 0, stream);
-    static int kslabs = -1;
-    if (kslabs < 0) {
-        const char *e = getenv("PASNL_GEMM_WS_KSLABS");
-        kslabs = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    if (kslabs && col_stats == nullptr && pasnl_gemm_rows_ws_kslabs_eligible(rows, k, n, A, lda))
-        return pasnl_gemm_rows_ws_kslabs(rows, k, n, A, lda, Bt, ldb, 0, C, ldc, stream);
     // mid-size layers with TMA-legal operands: both operands by TMA, any k (gemm_tma.cu)
     if (pasnl_gemm_rows_tma_eligible(rows, k, n, A, lda, Bt, ldb))
         return pasnl_gemm_rows_tma(rows, k, n, A, lda, Bt, ldb, C, ldc, col_stats, stream);

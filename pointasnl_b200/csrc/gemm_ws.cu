@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_rows_ws_kernel(const __grid_constant__ CUtensorMap amap, long rows, int k, int kpad, int n, long ntiles,
                     const float *__restrict__ W, long ldw, int w_kn, float *__restrict__ C, long ldc,
                     double *__restrict__ stats, const float *__restrict__ pro_scale, const float *__restrict__ pro_shift,
-                    int pro_act, int accumulate) {
+                    int pro_act) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t loaded[kStages], ready[kStages], empty[kStages], tfull[2], tempty[2];
     __shared__ uint32_t tmem_slot;
@@ -297,11 +297,6 @@ gemm_rows_ws_kernel(const __grid_constant__ CUtensorMap amap, long rows, int k, 
                 if (!have_shift) { shiftv = v[0]; have_shift = true; }
                 float *dst = C + (row0 + q * 32) * ldc + n0 + ch;
                 if (chv) {
-                    if (accumulate) {                          // C += (a second k slab of the same product)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (q * 32 + i < nv) v[i] += dst[(long)i * ldc];
-                    }
                     if (q * 32 + 32 <= nv) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -410,9 +405,9 @@ extern "C" int pasnl_gemm_rows_ws_wide_eligible(long rows, int k, int n, const v
 // C[rows, n] = f(A)[rows, k] . W.  W is [k][n] (w_kn != 0, pitch ldw) or [n][k] (w_kn == 0).  col_stats (2n doubles,
 // zero-initialised by the caller) or NULL: += per-column sum and sum of squares of C.  pro_scale / pro_shift (k floats
 // each) or NULL: f(a) = act(a * scale[col] + shift[col]), pro_act 0 none / 1 relu / 2 leaky_relu(0.2).
-static int gemm_rows_ws_launch(long rows, int k, int n, const float *A, long lda, const float *W, long ldw, int w_kn,
-                               float *C, long ldc, double *col_stats, const float *pro_scale, const float *pro_shift,
-                               int pro_act, int accumulate, void *stream) {
+extern "C" int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long lda, const float *W, long ldw, int w_kn,
+                                  float *C, long ldc, double *col_stats, const float *pro_scale, const float *pro_shift,
+                                  int pro_act, void *stream) {
     PASNL_CHECK_ARG(rows >= 0 && k >= 1 && n >= 1 && lda >= k && ldc >= n && (w_kn ? ldw >= n : ldw >= k));
     if (rows == 0) return PASNL_OK;
     PASNL_CHECK_ARG(A && W && C && (pasnl_gemm_rows_ws_eligible(rows, k, n, A, lda) ||
@@ -439,38 +434,6 @@ static int gemm_rows_ws_launch(long rows, int k, int n, const float *A, long lda
     cudaError_t e = cudaFuncSetAttribute(gws::gemm_rows_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     gws::gemm_rows_ws_kernel<<<grid, gws::kThreads, smem, st>>>(map, rows, k, kpad, n, ntiles, W, ldw, w_kn, C, ldc,
-                                                                col_stats, pro_scale, pro_shift, pro_act, accumulate);
+                                                                col_stats, pro_scale, pro_shift, pro_act);
     return pasnl_launch_status();
-}
-
-extern "C" int pasnl_gemm_rows_ws(long rows, int k, int n, const float *A, long lda, const float *W, long ldw, int w_kn,
-                                  float *C, long ldc, double *col_stats, const float *pro_scale, const float *pro_shift,
-                                  int pro_act, void *stream) {
-    return gemm_rows_ws_launch(rows, k, n, A, lda, W, ldw, w_kn, C, ldc, col_stats, pro_scale, pro_shift, pro_act, 0, stream);
-}
-
-// Contractions of 128 < k <= 256 with many output columns (the input gradient of the after_conv layer of a 256-channel
-// SA layer: 4096 x 256 -> 4096): <= 128-wide k slabs through the wide launch, the later slabs adding into C.
-// NOT routed to by default (pasnl_gemm_rows_tf32x3 and the Python layer do so only with PASNL_GEMM_WS_KSLABS=1): measured on
-// the cls step, the two persistent launches with their read-modify-write of C cost 0.1 ms/step more than the one-tile
-// kernel they replace.
-extern "C" int pasnl_gemm_rows_ws_kslabs_eligible(long rows, int k, int n, const void *A, long lda) {
-    if (k <= 128 || k > 256 || (k % 4) != 0) return 0;      // two slabs: C is written, then read and written once more
-    const int slabs = (k + 127) / 128, kslab = ((k + slabs - 1) / slabs + 3) / 4 * 4;
-    return pasnl_gemm_rows_ws_wide_eligible(rows, kslab, n, A, lda) &&
-           pasnl_gemm_rows_ws_wide_eligible(rows, k - (slabs - 1) * kslab, n, A, lda);
-}
-
-extern "C" int pasnl_gemm_rows_ws_kslabs(long rows, int k, int n, const float *A, long lda, const float *W, long ldw,
-                                         int w_kn, float *C, long ldc, void *stream) {
-    PASNL_CHECK_ARG(A && W && C && pasnl_gemm_rows_ws_kslabs_eligible(rows, k, n, A, lda));
-    const int slabs = (k + 127) / 128, kslab = ((k + slabs - 1) / slabs + 3) / 4 * 4;
-    for (int s = 0, k0 = 0; s < slabs; ++s, k0 += kslab) {
-        const int kk = s == slabs - 1 ? k - k0 : kslab;
-        const float *Ws = w_kn ? W + (long)k0 * ldw : W + k0;
-        const int rc = gemm_rows_ws_launch(rows, kk, n, A + k0, lda, Ws, ldw, w_kn, C, ldc, nullptr, nullptr, nullptr, 0,
-                                           s > 0 ? 1 : 0, stream);
-        if (rc != PASNL_OK) return rc;
-    }
-    return PASNL_OK;
 }

@@ -24,7 +24,7 @@ def run_ws(a, w, w_kn, stats=False, pro=None, act=0, ldc=None):
 
 
 @pytest.mark.parametrize("rows,k,n", [(40000, 128, 128), (37888, 64, 64), (50001, 36, 20), (41111, 100, 70),
-                                      (39000, 20, 128), (262144, 128, 128), (38000, 68, 17), (40000, 128, 6)])
+                                      (39000, 20, 128), (262144, 128, 128), (38000, 68, 17)])
 @pytest.mark.parametrize("w_kn", [False, True])
 def test_rows_ws_matches_fp64(cuda, rows, k, n, w_kn):
     torch.manual_seed(rows + k)
@@ -64,25 +64,6 @@ def test_rows_ws_wide_column_blocks_match_fp64(cuda, rows, k, n, w_kn):
     from pointasnl_b200 import _ops
     got = _ops.gemm_rows(a, wt, w_kn=w_kn)
     assert torch.equal(got, c[:, :n].contiguous())
-
-
-@pytest.mark.parametrize("rows,k,n", [(4096, 256, 4096), (5000, 252, 2052), (9000, 132, 1100)])
-@pytest.mark.parametrize("w_kn", [False, True])
-def test_rows_ws_k_slabs_accumulate_into_c(cuda, rows, k, n, w_kn):
-    """128 < k <= 256 onto many columns: two k slabs through the wide launch, the second adding into C.  (Routing to it
-    is opt-in, PASNL_GEMM_WS_KSLABS=1, because it measured slower on the step; the entry point is tested directly.)"""
-    from pointasnl_b200 import _lib, _ops
-    torch.manual_seed(rows + k)
-    a = torch.randn(rows, k, device=cuda)
-    w = torch.randn(k, n, device=cuda) / k ** 0.5
-    wt = w if w_kn else w.t().contiguous()
-    assert _lib.load().pasnl_gemm_rows_ws_kslabs_eligible(rows, k, n, a.data_ptr(), a.stride(0)) == 1
-    c = torch.full((rows, n + 4), 7.0, device=cuda)
-    _lib.call("pasnl_gemm_rows_ws_kslabs", rows, k, n, a.data_ptr(), a.stride(0), wt.data_ptr(), wt.stride(0),
-              1 if w_kn else 0, c.data_ptr(), n + 4, _ops._stream())
-    want = a.double() @ w.double()
-    assert float((c[:, :n].double() - want).abs().max()) / float(want.abs().max()) < 5e-6
-    assert bool((c[:, n:] == 7.0).all())
 
 
 @pytest.mark.parametrize("act", [0, 1, 2])
