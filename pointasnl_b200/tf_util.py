@@ -292,25 +292,12 @@ def conv1d(inputs, num_output_channels, kernel_size, scope, stride=1, padding="S
     return out
 
 
-class PreNorm:
-    """The output of a conv + batch-norm layer BEFORE the normalise + activate pass, with what a consumer kernel needs to
-    apply it on chip: y (raw GEMM output), scale / shift (act(y * scale + shift) is the layer's output), and gamma, beta,
-    mean, var for the way back (see _ops.BNActPointConv)."""
-
-    def __init__(self, y, gamma, beta, mean, var, scale, shift, eps, act):
-        self.y, self.gamma, self.beta, self.mean, self.var = y, gamma, beta, mean, var
-        self.scale, self.shift, self.eps, self.act = scale, shift, eps, act
-
-
 def conv2d_pair(inputs, channels, scopes, bn_decay=None, is_training=None, weight_decay=None, activation_fn=relu,
-                use_xavier=True, stddev=1e-3, pre_norm_out=None):
+                use_xavier=True, stddev=1e-3):
     """Two stacked conv2d([1,1], bn=True) layers -- the same variables, in the same order and scopes, as
     conv2d(conv2d(inputs, channels[0], scope=scopes[0]), channels[1], scope=scopes[1]) -- run as one fused pair on CUDA in
     training mode (_ops.DenseBNAct2: the activation between the two layers is never written to memory); otherwise the
-    two conv2d calls themselves.
-    pre_norm_out: optional predicate (rows, channels) -> bool of a consumer that can take the SECOND layer's output as a
-    PreNorm (normalise + activate applied inside the consumer's kernel); when it agrees and the shapes allow, a PreNorm
-    is returned instead of a tensor."""
+    two conv2d calls themselves."""
     code = _act_code(activation_fn)
     if not (inputs.is_cuda and bool(is_training) and code is not None and inputs.dtype == torch.float32):
         for c, sc in zip(channels, scopes):
@@ -333,11 +320,6 @@ def conv2d_pair(inputs, channels, scopes, bn_decay=None, is_training=None, weigh
                 var = store.get_variable("moving_variance", (c,), constant_init(1.0), trainable=False)
         args += [w.view(cin, c), bias, gamma, beta, mean, var]
         cin = c
-    if pre_norm_out is not None:
-        x2 = _ops._rows_view(inputs, inputs.shape[-1])
-        if _ops.pair_plan(x2, channels[0], channels[1]) and pre_norm_out(x2.shape[0], channels[1]):
-            y, mean2, var2, scale2, shift2 = _ops.DenseBNAct2.apply(inputs, *args, decay, 1e-3, code, code, True, True)
-            return PreNorm(y, args[8], args[9], mean2, var2, scale2, shift2, 1e-3, code)
     return _ops.DenseBNAct2.apply(inputs, *args, decay, 1e-3, code, code, True)
 
 
