@@ -580,6 +580,10 @@ def main():
             e["ms_per_step"] += r["ms_per_step"]
             if e["largest"] is None or r["avg_us"] > e["largest"]["avg_us"]:
                 e["largest"] = {"dims": r["dims"], "avg_us": r["avg_us"]}
+                if r["name"] == "pasnl_fps" and r["avg_us"] > 0:     # rounds/s and the on-chip sweep rate
+                    b_, n_, m_ = r["dims"][0:3]
+                    e["largest"]["rounds_per_s"] = m_ / (r["avg_us"] * 1e-6)
+                    e["largest"]["onchip_sweep_gbs"] = 16.0 * b_ * m_ * n_ / (r["avg_us"] * 1e-6) / 1e9
             continue
         by_name[op_of(r["name"])] = by_name.get(op_of(r["name"]), 0.0) + r["ms_per_step"]
     top_name = max(by_name, key=by_name.get)
