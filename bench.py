@@ -580,8 +580,8 @@ def main():
             e["ms_per_step"] += r["ms_per_step"]
             if e["largest"] is None or r["avg_us"] > e["largest"]["avg_us"]:
                 e["largest"] = {"dims": r["dims"], "avg_us": r["avg_us"]}
-                if r["name"] == "pasnl_fps" and r["avg_us"] > 0:     # rounds/s and the on-chip sweep rate
-                    b_, n_, m_ = r["dims"][0:3]
+                if r["name"] == "pasnl_fps" and r["avg_us"] > 0 and len(r["dims"]) >= 3:
+                    b_, n_, m_ = (float(v) for v in r["dims"][0:3])  # rounds/s and the on-chip sweep rate
                     e["largest"]["rounds_per_s"] = m_ / (r["avg_us"] * 1e-6)
                     e["largest"]["onchip_sweep_gbs"] = 16.0 * b_ * m_ * n_ / (r["avg_us"] * 1e-6) / 1e9
             continue
