@@ -591,6 +591,11 @@ def main():
     if top["bound"] == "tensor":
         roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": top["tflops"] / peaks["bf16_tflops"]}
+    elif top["bound"] == "fp32":
+        # the brute-force distance kernels (k-NN / ball query / three_nn at SemanticKITTI size) are bound by the fp32 FMA
+        # pipe, not by HBM or the tensor cores: reported against the SIMT peak (148 SMs x 128 lanes x 2 x 1965 MHz)
+        roof = {"bound": "fp32", "achieved": top["tflops"], "peak": FP32_SIMT_TFLOPS, "unit": "TFLOP/s",
+                "frac": top["tflops"] / FP32_SIMT_TFLOPS}
     else:
         roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": top["gbs"] / peaks["hbm_gbs"]}
