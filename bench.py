@@ -211,7 +211,7 @@ def algorithmic_work(name, a):
     if name == "pasnl_bn_act_bwd":       # reduce reads y, dout; apply reads y, dout, writes dy
         rows, c = a[0:2]
         return 20 * rows * c, 16 * rows * c, "hbm"
-    if name == "pasnl_gemm_rows_ws":
+    if name in ("pasnl_gemm_rows_ws", "pasnl_gemm_rows_tma"):
         rows, k, n = a[0:3]
         return 4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n, gemm_bound(4 * rows * (k + n) + 4 * k * n, 2 * rows * k * n)
     if name in ("pasnl_pointconv_fwd", "pasnl_pointconv_fwd_bn"):    # x (G,K,C) + w (G,K,32) in, (G,C,32) out
@@ -229,6 +229,12 @@ def algorithmic_work(name, a):
     if name == "pasnl_maxpool_k_scatter":   # mask + grad_out in; ~one 32-byte sector read-modify-written per (g, c)
         g, k, c = a[0:3]
         return 12 * g * c + 64 * g * c, g * c, "hbm"
+    if name == "pasnl_take_cols":        # reads rows x nc (strided), writes rows x nc
+        rows, nc = a[0:2]
+        return 8 * rows * nc, 0, "hbm"
+    if name == "pasnl_transpose_batched":   # <= count x max_tiles 32x32 tiles, read + written (an upper bound: the table
+        count, max_tiles = a[0], a[2]       # with the true sizes lives on the device)
+        return 8 * 1024 * count * max_tiles if isinstance(max_tiles, int) else 0, 0, "hbm"
     if name == "pasnl_add_cols":
         rows, nc = a[0:2]
         return 12 * rows * nc, rows * nc, "hbm"
@@ -567,7 +573,7 @@ def main():
     # (the rows GEMM is one op with two C entry points: pasnl_gemm_rows_tf32x3 routes tall layers to pasnl_gemm_rows_ws and
     #  the Python layer calls the latter directly when it wants the [k][n] weight layout -- they are ranked together)
     def op_of(name):
-        if name in ("pasnl_gemm_rows_tf32x3", "pasnl_gemm_rows_ws"):
+        if name in ("pasnl_gemm_rows_tf32x3", "pasnl_gemm_rows_ws", "pasnl_gemm_rows_tma"):
             return "pasnl_gemm_rows"
         return "pasnl_gemm_wgrad" if name in ("pasnl_gemm_wgrad_tf32x3", "pasnl_gemm_wgrad_tma") else name
     # Farthest point sampling is a latency chain (npoint dependent rounds on one CTA / cluster per cloud, a few KB of
