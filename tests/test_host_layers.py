@@ -32,3 +32,29 @@ def test_nonlocal_cell_concat_mode_matches_reference_python_on_cpu():
     for k in g.files:
         if k.startswith("moving/"):
             np.testing.assert_allclose(store.variables()[k[7:]].numpy(), g[k], rtol=1e-4, atol=1e-6)
+
+
+def test_conv2d_pair_creates_the_variables_of_two_conv2d_calls_and_matches_them_on_cpu():
+    """tf_util.conv2d_pair (the fused conv0 -> conv1 pair of a local cell on CUDA) must be indistinguishable from two
+    conv2d calls: same variable names in the same creation order, same values, same moving averages."""
+    from pointasnl_b200 import tf_util
+    x = torch.randn(2, 5, 4, 7)
+    outs, names, moving = [], [], []
+    for pair in (False, True):
+        store = tf_util.VariableStore("cpu", init_fn=lambda full, shape, leaf: golden_init(full, shape, leaf))
+        with store.as_default(), tf_util.variable_scope("layer"):
+            if pair:
+                y = tf_util.conv2d_pair(x, [6, 5], ("conv0", "conv1"), bn_decay=0.9, is_training=True, weight_decay=0.1)
+            else:
+                y = x
+                for i, c in enumerate([6, 5]):
+                    y = tf_util.conv2d(y, c, [1, 1], padding="VALID", stride=[1, 1], bn=True, is_training=True,
+                                       scope="conv%d" % i, bn_decay=0.9, weight_decay=0.1)
+        outs.append(y)
+        names.append(list(store.variables()))
+        moving.append({n: v.clone() for n, v in store.variables().items() if "moving" in n})
+    assert names[0] == names[1]
+    assert names[0][:2] == ["layer/conv0/weights", "layer/conv0/biases"] and "layer/conv1/bn/moving_variance" in names[0]
+    torch.testing.assert_close(outs[0], outs[1], rtol=0, atol=0)
+    for n in moving[0]:
+        torch.testing.assert_close(moving[0][n], moving[1][n], rtol=0, atol=0)
